@@ -1,0 +1,869 @@
+// engine.cu -- host side of libnano_b200.so: model-file parser, HBM layout/upload, CUDA-graph token
+// step, and the C-ABI declared in include/nano_b200.h.
+//
+// HBM layout (free to differ from the file; the contract is the file format and the C API):
+//   per layer, one fused row-major matrix per launch so each weight byte is streamed exactly once:
+//     QKV  : rows = q_dim + 2*kv_dim  (wq rows, then wk, then wv)          n = n_embd
+//     O    : rows = n_embd                                                  n = q_dim
+//     W13  : rows = 2*n_hidden, row 2i = w1[i], row 2i+1 = w3[i]            n = n_embd
+//     W2   : rows = n_embd                                                  n = n_hidden
+//   CLS/embedding : rows = vocab (one copy when tied)                       n = n_embd
+//   Q80 : int8 codes [rows][n] + fp32 scales [rows][n/gs]
+//   Q4K : nibble plane [rows][n/2] (16-byte groups, 128-bit loads) + 20-byte side records
+//         {s_scale, s_bias, sb[12]} [rows][n/256]; the constant 12 bytes {tag,len,meta} of each 160-byte
+//         file block are dropped (148 B/block streamed instead of 160)
+//   F32 : float [rows][n]
+//   KV cache : [L][KV][max_seq][hd] fp32, head-major (a split-KV CTA reads one contiguous stream);
+//              the reference's layout is [L][pos][kv_dim] (infer.c:46-51)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nano_b200.h"
+#include "kernels.cuh"
+
+using namespace nb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(NB200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline uint32_t rd_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t rd_u64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+struct Mat {            // one fused device matrix
+    void *w = nullptr;  // codes / floats / nibble plane
+    void *aux = nullptr;
+    uint32_t rows = 0, n = 0;
+};
+
+// staging -> (nibble plane, side records) with a row mapping dst_row = row_off + src_row * row_stride
+__global__ void k_q4k_split(const uint8_t *__restrict__ blocks, uint64_t nblocks, uint32_t bpr, uint8_t *nib, uint8_t *side,
+                            uint32_t row_off, uint32_t row_stride) {
+    const uint64_t total = nblocks * 37;       // 32 nibble words + 5 side words per block
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = i / 37; const uint32_t wd = (uint32_t)(i % 37);
+        const uint64_t srow = b / bpr; const uint32_t j = (uint32_t)(b % bpr);
+        const uint64_t drow = row_off + srow * row_stride;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(blocks + b * 160);
+        if (wd < 32) reinterpret_cast<uint32_t *>(nib + (drow * bpr + j) * 128)[wd] = src[8 + wd];
+        else reinterpret_cast<uint32_t *>(side + (drow * bpr + j) * 20)[wd - 32] = src[3 + (wd - 32)];
+    }
+}
+
+}  // namespace
+
+struct nb200_engine {
+    Dims d{};
+    uint32_t flags = 0;
+    int device = 0, num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::vector<Mat> qkv, wo, w13, w2;
+    Mat cls, emb;
+    float *norm_attn = nullptr, *norm_ffn = nullptr, *norm_final = nullptr, *qnorm = nullptr, *knorm = nullptr;
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+    float *x = nullptr, *q = nullptr, *kraw = nullptr, *xba = nullptr, *hb = nullptr, *logits = nullptr;
+    float *kc = nullptr, *vc = nullptr, *att_exact = nullptr;
+    float *ws_m = nullptr, *ws_l = nullptr, *ws_acc = nullptr;
+    uint32_t *tickets = nullptr, *ids_dev = nullptr, *cls_idx = nullptr;
+    float *cls_val = nullptr;
+    uint8_t *seen = nullptr;
+    DevState *st = nullptr;
+    DevState *st_host = nullptr;      // pinned
+    uint32_t *tok_host = nullptr;     // pinned result slot
+    int8_t *dump_codes = nullptr; float *dump_scales = nullptr;
+    uint32_t nsplit_max = 1, chunk_cap = 32, attn_smem = 0, cls_grid = 1;
+    cudaGraphExec_t graph = nullptr;
+    bool use_pdl = true;
+    uint64_t launches = 0, weight_bytes = 0;
+    uint32_t launches_per_token = 0;
+    std::vector<uint32_t> seen_mirror;   // ids whose seen[] flag is set, by position
+    bool seen_valid = false;
+    std::vector<void *> allocs;
+    uint32_t tp_rank = 0, tp_size = 1;
+};
+
+namespace {
+
+int dmalloc(nb200_engine *e, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t err = cudaMalloc(p, bytes);
+    if (err != cudaSuccess) return fail(NB200_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    e->allocs.push_back(*p);
+    return 0;
+}
+#define DM(ptr, bytes) do { int r_ = dmalloc(e, (void **)&(ptr), (bytes)); if (r_) return r_; } while (0)
+
+// ---------------- kernel launch plumbing ----------------
+template <typename Args>
+int launch(nb200_engine *e, void (*kern)(const Args), dim3 grid, dim3 block, size_t smem, const Args &args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = e ? e->stream : nullptr;
+    cudaLaunchAttribute attr[1];
+    if (e && e->use_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaLaunchKernelEx(&cfg, kern, args));
+    if (e) e->launches++;
+    return 0;
+}
+
+typedef void (*MatvecKern)(const MatvecArgs);
+
+template <int QUANT, int EPI>
+MatvecKern pick_matvec(int rb, int lpg) {
+    if (QUANT == 0x80) {
+#define NB_PICK(RB_, L_) if (rb == RB_ && lpg == L_) return k_matvec<QUANT, EPI, RB_, L_>;
+        NB_PICK(2, 2) NB_PICK(2, 4) NB_PICK(2, 8) NB_PICK(2, 16)
+        NB_PICK(4, 2) NB_PICK(4, 4) NB_PICK(4, 8) NB_PICK(4, 16)
+#undef NB_PICK
+        return nullptr;
+    }
+    if (rb == 2) return k_matvec<QUANT, EPI, 2, 8>;
+    return k_matvec<QUANT, EPI, 4, 8>;
+}
+
+template <int EPI>
+MatvecKern pick_matvec_q(uint32_t quant, int rb, int lpg) {
+    if (quant == 0x00u) return pick_matvec<0x00, EPI>(rb, lpg);
+    if (quant == 0x80u) return pick_matvec<0x80, EPI>(rb, lpg);
+    return pick_matvec<0x42, EPI>(rb, lpg);
+}
+
+int grid_mult() {
+    static int m = -1;
+    if (m < 0) { const char *s = getenv("NB200_GRID_MULT"); m = s ? atoi(s) : 1; if (m < 1) m = 1; }
+    return m;
+}
+
+// one fused matvec launch
+int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, int num_sms) {
+    const Dims &d = a.d;
+    a.w = m.w; a.w_aux = m.aux; a.rows = m.rows; a.n = m.n;
+    const uint32_t smem = act_smem_bytes(d.quant, m.n, d.gs ? d.gs : 1, d.exact && norm);
+    if (d.quant == 0x00u && d.exact) {
+        MatvecKern k = nullptr;
+        switch (epi) {
+            case EPI_STORE: k = k_matvec_f32_exact<EPI_STORE>; break;
+            case EPI_QKV: k = k_matvec_f32_exact<EPI_QKV>; break;
+            case EPI_RESID: k = k_matvec_f32_exact<EPI_RESID>; break;
+            case EPI_SWIGLU: k = k_matvec_f32_exact<EPI_SWIGLU>; break;
+            default: break;     // CLS keeps the fast kernel below (argmax fused); exactness handled by caller
+        }
+        if (k) {
+            const uint32_t units = (epi == EPI_SWIGLU) ? m.rows / 2 : m.rows;
+            const uint32_t grid = (units + 255) / 256;
+            return launch<MatvecArgs>(e, k, dim3(grid), dim3(256), smem, a);
+        }
+    }
+    const uint32_t total_warps = (uint32_t)num_sms * grid_mult() * kWarps;
+    int rb = (m.rows >= total_warps * 8) ? 4 : 2;
+    const int lpg = (d.quant == 0x80u) ? (int)(d.gs / 16) : 8;
+    MatvecKern k = nullptr;
+    switch (epi) {
+        case EPI_STORE: k = pick_matvec_q<EPI_STORE>(d.quant, rb, lpg); break;
+        case EPI_QKV: k = pick_matvec_q<EPI_QKV>(d.quant, rb, lpg); break;
+        case EPI_RESID: k = pick_matvec_q<EPI_RESID>(d.quant, rb, lpg); break;
+        case EPI_SWIGLU: k = pick_matvec_q<EPI_SWIGLU>(d.quant, rb, lpg); break;
+        case EPI_CLS: k = pick_matvec_q<EPI_CLS>(d.quant, rb, lpg); break;
+    }
+    if (!k) return fail(NB200_EINVAL, "no matvec kernel for quant=0x%x gs=%u", d.quant, d.gs);
+    const uint32_t nblocks = (m.rows + rb - 1) / rb;
+    uint32_t grid = (nblocks + kWarps - 1) / kWarps;
+    const uint32_t cap = (uint32_t)num_sms * grid_mult();
+    if (grid > cap) grid = cap;
+    if (epi == EPI_CLS && e) { if (grid > e->cls_grid) grid = e->cls_grid; }
+    return launch<MatvecArgs>(e, k, dim3(grid), dim3(kThreads), smem, a);
+}
+
+MatvecArgs base_args(nb200_engine *e) {
+    MatvecArgs a{};
+    a.d = e->d; a.st = e->st;
+    return a;
+}
+
+int run_embed(nb200_engine *e) {
+    EmbedArgs a{};
+    a.w = e->emb.w; a.w_aux = e->emb.aux; a.x = e->x; a.ids = e->ids_dev; a.st = e->st; a.d = e->d;
+    return launch<EmbedArgs>(e, k_embed, dim3(1), dim3(256), 0, a);
+}
+
+int run_layer(nb200_engine *e, uint32_t l) {
+    const Dims &d = e->d;
+    const size_t kvl = (size_t)d.KV * d.max_seq * d.hd;
+    int r;
+    {   // F1: rmsnorm + quantise + QKV matvec + KV store
+        MatvecArgs a = base_args(e);
+        a.src = e->x; a.gain = e->norm_attn + (size_t)l * d.E;
+        a.out = e->q; a.out_k = e->kraw; a.out_v = e->vc + l * kvl;
+        a.dump_codes = e->dump_codes; a.dump_scales = e->dump_scales;
+        if ((r = run_matvec(e, EPI_QKV, e->qkv[l], a, true, e->num_sms))) return r;
+    }
+    if (!d.exact) {   // F2: head-norm + RoPE + split-KV attention
+        AttnArgs a{};
+        a.q = e->q; a.kraw = e->kraw; a.kc = e->kc + l * kvl; a.vc = e->vc + l * kvl;
+        a.qnorm = e->qnorm ? e->qnorm + (size_t)l * d.hd : nullptr;
+        a.knorm = e->knorm ? e->knorm + (size_t)l * d.hd : nullptr;
+        a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.xba = e->xba;
+        a.ws_m = e->ws_m; a.ws_l = e->ws_l; a.ws_acc = e->ws_acc; a.ticket = e->tickets;
+        a.st = e->st; a.nsplit_max = e->nsplit_max; a.chunk_cap = e->chunk_cap; a.d = d;
+        if ((r = launch<AttnArgs>(e, k_attention, dim3(e->nsplit_max, d.KV), dim3(kAttnThreads), e->attn_smem, a))) return r;
+    } else {
+        AttnExactArgs a{};
+        a.q = e->q; a.kraw = e->kraw; a.kc = e->kc + l * kvl; a.vc = e->vc + l * kvl;
+        a.qnorm = e->qnorm ? e->qnorm + (size_t)l * d.hd : nullptr;
+        a.knorm = e->knorm ? e->knorm + (size_t)l * d.hd : nullptr;
+        a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.xba = e->xba; a.att = e->att_exact; a.st = e->st; a.d = d;
+        if ((r = launch<AttnExactArgs>(e, k_attention_exact, dim3(d.H), dim3(kAttnThreads), 2 * d.hd * 4, a))) return r;
+    }
+    {   // F3: quantise(xba) + O matvec + residual
+        MatvecArgs a = base_args(e);
+        a.src = e->xba; a.gain = nullptr; a.out = e->x;
+        if ((r = run_matvec(e, EPI_RESID, e->wo[l], a, false, e->num_sms))) return r;
+    }
+    {   // F4: rmsnorm + quantise + W1|W3 matvec + SwiGLU
+        MatvecArgs a = base_args(e);
+        a.src = e->x; a.gain = e->norm_ffn + (size_t)l * d.E; a.out = e->hb;
+        if ((r = run_matvec(e, EPI_SWIGLU, e->w13[l], a, true, e->num_sms))) return r;
+    }
+    {   // F5: quantise(hb) + W2 matvec + residual
+        MatvecArgs a = base_args(e);
+        a.src = e->hb; a.gain = nullptr; a.out = e->x;
+        if ((r = run_matvec(e, EPI_RESID, e->w2[l], a, false, e->num_sms))) return r;
+    }
+    return 0;
+}
+
+int run_classifier(nb200_engine *e) {
+    MatvecArgs a = base_args(e);
+    a.src = e->x; a.gain = e->norm_final; a.out = e->logits;
+    if (e->d.quant == 0x00u && e->d.exact) {
+        int r = run_matvec(e, EPI_STORE, e->cls, a, true, e->num_sms);
+        if (r) return r;
+        FinalizeArgs f{e->logits, e->d.V, e->seen, e->seen, e->ids_dev, e->st};
+        return launch<FinalizeArgs>(e, k_cls_finalize, dim3(1), dim3(1024), 0, f);
+    }
+    a.st_rw = e->st; a.seen = e->seen; a.seen_rw = e->seen; a.cls_val = e->cls_val; a.cls_idx = e->cls_idx; a.ids = e->ids_dev;
+    return run_matvec(e, EPI_CLS, e->cls, a, true, e->num_sms);
+}
+
+int run_token(nb200_engine *e) {
+    int r;
+    if ((r = run_embed(e))) return r;
+    for (uint32_t l = 0; l < e->d.L; l++) if ((r = run_layer(e, l))) return r;
+    return run_classifier(e);
+}
+
+int launch_token(nb200_engine *e) {
+    if (e->graph) {
+        CK(cudaGraphLaunch(e->graph, e->stream));
+        e->launches += e->launches_per_token;
+        return 0;
+    }
+    return run_token(e);
+}
+
+int capture_graph(nb200_engine *e) {
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const uint64_t before = e->launches;
+    int r = run_token(e);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->launches_per_token = (uint32_t)(e->launches - before);
+    e->launches = before;
+    if (r) { if (g) cudaGraphDestroy(g); return r; }
+    if (ce != cudaSuccess) return fail(NB200_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) { e->graph = nullptr; return fail(NB200_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce)); }
+    return 0;
+}
+
+// ---------------- uploads ----------------
+int upload_rows(void *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, size_t height) {
+    CK(cudaMemcpy2D(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+struct Q80Src { const uint8_t *q, *s; };
+
+int alloc_mat(nb200_engine *e, Mat &m, uint32_t rows, uint32_t n) {
+    const Dims &d = e->d;
+    m.rows = rows; m.n = n;
+    size_t wb, ab;
+    if (d.quant == 0x00u) { wb = (size_t)rows * n * 4; ab = 0; }
+    else if (d.quant == 0x80u) { wb = (size_t)rows * n; ab = (size_t)rows * (n / d.gs) * 4; }
+    else { wb = (size_t)rows * n / 2; ab = (size_t)rows * (n / 256) * 20; }
+    DM(m.w, wb + 64);
+    if (ab) DM(m.aux, ab + 64);
+    e->weight_bytes += wb + ab;
+    return 0;
+}
+
+// copy `srows` source rows into the fused matrix at dst_row = off + i*stride
+int put_rows(nb200_engine *e, Mat &m, const uint8_t *w, const uint8_t *aux, uint32_t srows, uint32_t off, uint32_t stride,
+             uint8_t *staging) {
+    const Dims &d = e->d;
+    const uint32_t n = m.n;
+    if (d.quant == 0x00u) {
+        return upload_rows((uint8_t *)m.w + (size_t)off * n * 4, (size_t)stride * n * 4, w, (size_t)n * 4, (size_t)n * 4, srows);
+    } else if (d.quant == 0x80u) {
+        const uint32_t G = n / d.gs;
+        int r = upload_rows((uint8_t *)m.w + (size_t)off * n, (size_t)stride * n, w, n, n, srows);
+        if (r) return r;
+        return upload_rows((uint8_t *)m.aux + (size_t)off * G * 4, (size_t)stride * G * 4, aux, (size_t)G * 4, (size_t)G * 4, srows);
+    } else {
+        const uint32_t bpr = n / 256;
+        const uint64_t nblocks = (uint64_t)srows * bpr;
+        CK(cudaMemcpy(staging, w, nblocks * 160, cudaMemcpyHostToDevice));
+        const uint64_t total = nblocks * 37;
+        const uint32_t grid = (uint32_t)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+        k_q4k_split<<<grid, 256>>>(staging, nblocks, bpr, (uint8_t *)m.w, (uint8_t *)m.aux, off, stride);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        return 0;
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+const char *nb200_last_error(void) { return g_err.c_str(); }
+
+int nb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void nb200_engine_destroy(nb200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->st_host) cudaFreeHost(e->st_host);
+    if (e->tok_host) cudaFreeHost(e->tok_host);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
+                        uint32_t flags) {
+    if (!out || !img || image_bytes < 260 || max_seq_len == 0) return fail(NB200_EINVAL, "bad arguments");
+    *out = nullptr;
+    if (nb200_device_count() <= 0) return fail(NB200_ENODEV, "no CUDA device: nano_b200 has no CPU path");
+    if (rd_u32(img) != 0x42443453u || rd_u32(img + 4) != 0x55524c4du) return fail(NB200_EINVAL, "bad magic (not a BD4SURLM file)");
+    CK(cudaSetDevice(device));
+    nb200_engine *e = new nb200_engine();
+    struct Guard { nb200_engine *e; bool ok = false; ~Guard() { if (!ok) nb200_engine_destroy(e); } } guard{e};
+    e->device = device; e->flags = flags;
+    e->use_pdl = !(flags & NB200_FLAG_NO_PDL);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    // ---- header (infer.c:231-256) ----
+    Dims &d = e->d;
+    d.arch = rd_u32(img + 16);
+    d.block_size = rd_u32(img + 24); d.V = rd_u32(img + 28); d.L = rd_u32(img + 32); d.E = rd_u32(img + 36);
+    d.H = rd_u32(img + 40); d.KV = rd_u32(img + 44); d.F = rd_u32(img + 48);
+    const uint32_t tied = rd_u32(img + 52);
+    uint32_t head_dim = rd_u32(img + 56);
+    const uint32_t qt = rd_u32(img + 60);
+    d.quant = (qt == 0x00u || qt == 0x80u || qt == 0x42u) ? qt : 0x80u;
+    d.gs = rd_u32(img + 64);
+    d.exact = (flags & NB200_FLAG_EXACT) ? 1u : 0u;
+    if (!d.L || !d.E || !d.H || !d.KV || !d.F || !d.V || d.H % d.KV) return fail(NB200_EINVAL, "bad model dimensions");
+    if (d.arch != 3u) head_dim = d.E / d.H;
+    d.hd = head_dim;
+    d.q_dim = (d.arch == 3u) ? d.hd * d.H : d.E;
+    d.kv_dim = (d.arch == 3u) ? d.hd * d.KV : (d.E * d.KV) / d.H;
+    d.kv_mul = d.H / d.KV;
+    d.max_seq = max_seq_len;
+    if (d.hd % 4 || d.hd > 512 || d.hd == 0) return fail(NB200_EINVAL, "head_dim %u unsupported (need multiple of 4, <= 512)", d.hd);
+    if (d.quant == 0x00u && (d.E % 4 || d.q_dim % 4 || d.F % 4)) return fail(NB200_EINVAL, "F32 path needs dims %% 4 == 0");
+    if (d.quant == 0x80u) {
+        if (d.gs != 32 && d.gs != 64 && d.gs != 128 && d.gs != 256) return fail(NB200_EINVAL, "Q80 group size %u unsupported (32/64/128/256)", d.gs);
+        if (d.E % d.gs || d.q_dim % d.gs || d.F % d.gs) return fail(NB200_EINVAL, "Q80 dims must be multiples of the group size");
+    }
+    if (d.quant == 0x42u && (d.E % 256 || d.q_dim % 256 || d.F % 256))
+        return fail(NB200_EINVAL, "Q4K needs n %% 256 == 0 (the reference's partial-block offset is wrong otherwise, tensor.c:307)");
+    if (d.quant != 0x80u) d.gs = (d.quant == 0x42u) ? 32 : 1;
+
+    // ---- parameter map (infer.c:100-217) ----
+    const uint32_t tok_bytes = rd_u32(img + 256);
+    const uint8_t *cur = img + 256 + tok_bytes;
+    const uint8_t *end = img + image_bytes;
+    const uint64_t L = d.L, E = d.E, V = d.V, F = d.F, QD = d.q_dim, KD = d.kv_dim;
+    auto need = [&](uint64_t bytes) { return (uint64_t)(end - cur) >= bytes; };
+    if (cur > end || !need((2 * L + 1) * E * 4)) return fail(NB200_EINVAL, "file truncated (norms)");
+    DM(e->norm_attn, L * E * 4); DM(e->norm_ffn, L * E * 4); DM(e->norm_final, E * 4);
+    CK(cudaMemcpy(e->norm_attn, cur, L * E * 4, cudaMemcpyHostToDevice)); cur += L * E * 4;
+    CK(cudaMemcpy(e->norm_ffn, cur, L * E * 4, cudaMemcpyHostToDevice)); cur += L * E * 4;
+    CK(cudaMemcpy(e->norm_final, cur, E * 4, cudaMemcpyHostToDevice)); cur += E * 4;
+
+    const uint64_t rows[7] = {QD, KD, KD, E, F, E, F};
+    const uint64_t cols[7] = {E, E, E, QD, E, F, E};
+    // source pointers per tensor kind and layer
+    std::vector<const uint8_t *> src_w[7], src_a[7];
+    const uint8_t *emb_w = nullptr, *emb_a = nullptr;
+    if (d.quant == 0x00u) {
+        if (!need(V * E * 4)) return fail(NB200_EINVAL, "file truncated (embedding)");
+        emb_w = cur; cur += V * E * 4;
+        for (int t = 0; t < 7; t++) {
+            if (!need(L * rows[t] * cols[t] * 4)) return fail(NB200_EINVAL, "file truncated (tensor %d)", t);
+            for (uint64_t l = 0; l < L; l++) { src_w[t].push_back(cur); src_a[t].push_back(nullptr); cur += rows[t] * cols[t] * 4; }
+        }
+    } else if (d.quant == 0x80u) {
+        auto take = [&](uint64_t each, const uint8_t *&w, const uint8_t *&a) {
+            w = cur; cur += each; a = cur; cur += (each / d.gs) * 4;
+        };
+        if (!need(V * E + V * E / d.gs * 4)) return fail(NB200_EINVAL, "file truncated (embedding)");
+        take(V * E, emb_w, emb_a);
+        for (int t = 0; t < 7; t++) {
+            const uint64_t each = rows[t] * cols[t];
+            if (!need(L * (each + each / d.gs * 4))) return fail(NB200_EINVAL, "file truncated (tensor %d)", t);
+            for (uint64_t l = 0; l < L; l++) { const uint8_t *w, *a; take(each, w, a); src_w[t].push_back(w); src_a[t].push_back(a); }
+        }
+    } else {
+        auto frame = [&](const uint8_t *&blocks, uint64_t expect_blocks) -> int {
+            if (!need(44)) return fail(NB200_EINVAL, "file truncated (Q4K frame)");
+            const uint64_t total = rd_u64(cur);
+            const uint32_t nblk = rd_u32(cur + 40);
+            if (nblk != expect_blocks || total != 44 + (uint64_t)nblk * 160 || !need(total))
+                return fail(NB200_EINVAL, "unexpected Q4K tensor frame (blocks %u, expected %llu)", nblk, (unsigned long long)expect_blocks);
+            blocks = cur + 44; cur += total;
+            return 0;
+        };
+        int r;
+        if ((r = frame(emb_w, V * (E / 256)))) return r;
+        for (int t = 0; t < 7; t++) {
+            const uint8_t *blocks;
+            const uint64_t per_layer = rows[t] * (cols[t] / 256);
+            if ((r = frame(blocks, L * per_layer))) return r;
+            for (uint64_t l = 0; l < L; l++) { src_w[t].push_back(blocks + l * per_layer * 160); src_a[t].push_back(nullptr); }
+        }
+    }
+    if (d.arch == 2u) cur += L * (QD + 2 * KD) * 4;     // Qwen2 biases: parsed, never applied (infer.c:175-179, 788-790)
+    if (d.arch == 3u) {
+        if (!need(2 * L * d.hd * 4)) return fail(NB200_EINVAL, "file truncated (q/k norm)");
+        DM(e->qnorm, L * d.hd * 4); DM(e->knorm, L * d.hd * 4);
+        CK(cudaMemcpy(e->qnorm, cur, L * d.hd * 4, cudaMemcpyHostToDevice)); cur += L * d.hd * 4;
+        CK(cudaMemcpy(e->knorm, cur, L * d.hd * 4, cudaMemcpyHostToDevice)); cur += L * d.hd * 4;
+    }
+    {   // RoPE tables: rows [0, min(block_size, max_seq)) are the only ones a context of max_seq can index
+        const uint32_t half = d.hd / 2;
+        const uint32_t nrows = d.block_size < d.max_seq ? d.block_size : d.max_seq;
+        const size_t tb = (size_t)nrows * half * 4;
+        DM(e->rope_cos, tb); DM(e->rope_sin, tb);
+        if (d.arch == 3u) {   // rebuilt with theta = 1e6 on the host libm, exactly infer.c:189-204
+            std::vector<float> c((size_t)nrows * half), s((size_t)nrows * half), fr(half);
+            for (uint32_t i = 0; i < half; i++) fr[i] = 1.0f / powf(1000000.0f, (float)(i * 2) / (float)d.hd);
+            for (uint32_t p = 0; p < nrows; p++)
+                for (uint32_t i = 0; i < half; i++) { c[(size_t)p * half + i] = cosf(p * fr[i]); s[(size_t)p * half + i] = sinf(p * fr[i]); }
+            CK(cudaMemcpy(e->rope_cos, c.data(), tb, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(e->rope_sin, s.data(), tb, cudaMemcpyHostToDevice));
+            cur += 2 * (size_t)d.block_size * half * 4;      // the reference skips a table it does not read
+        } else {
+            const size_t full = (size_t)d.block_size * half * 4;
+            if (!need(2 * full)) return fail(NB200_EINVAL, "file truncated (RoPE table)");
+            CK(cudaMemcpy(e->rope_cos, cur, tb, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(e->rope_sin, cur + full, tb, cudaMemcpyHostToDevice));
+            cur += 2 * full;
+        }
+    }
+    const uint8_t *cls_w = nullptr, *cls_a = nullptr;
+    if (d.quant == 0x80u && !tied) {
+        if (cur > end || !need(V * E + V * E / d.gs * 4)) return fail(NB200_EINVAL, "file truncated (classifier)");
+        cls_w = cur; cls_a = cur + V * E;
+    }
+
+    // ---- upload with re-layout ----
+    uint8_t *staging = nullptr;
+    if (d.quant == 0x42u) {
+        uint64_t mx = V * (E / 256);
+        for (int t = 0; t < 7; t++) { const uint64_t pl = rows[t] * (cols[t] / 256); if (pl > mx) mx = pl; }
+        CK(cudaMalloc(&staging, mx * 160));
+    }
+    struct StagingFree { uint8_t *p; ~StagingFree() { if (p) cudaFree(p); } } sfree{staging};
+    int r;
+    e->qkv.resize(L); e->wo.resize(L); e->w13.resize(L); e->w2.resize(L);
+    for (uint64_t l = 0; l < L; l++) {
+        if ((r = alloc_mat(e, e->qkv[l], (uint32_t)(QD + 2 * KD), (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->qkv[l], src_w[0][l], src_a[0][l], (uint32_t)QD, 0, 1, staging))) return r;
+        if ((r = put_rows(e, e->qkv[l], src_w[1][l], src_a[1][l], (uint32_t)KD, (uint32_t)QD, 1, staging))) return r;
+        if ((r = put_rows(e, e->qkv[l], src_w[2][l], src_a[2][l], (uint32_t)KD, (uint32_t)(QD + KD), 1, staging))) return r;
+        if ((r = alloc_mat(e, e->wo[l], (uint32_t)E, (uint32_t)QD))) return r;
+        if ((r = put_rows(e, e->wo[l], src_w[3][l], src_a[3][l], (uint32_t)E, 0, 1, staging))) return r;
+        if ((r = alloc_mat(e, e->w13[l], (uint32_t)(2 * F), (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->w13[l], src_w[4][l], src_a[4][l], (uint32_t)F, 0, 2, staging))) return r;
+        if ((r = put_rows(e, e->w13[l], src_w[6][l], src_a[6][l], (uint32_t)F, 1, 2, staging))) return r;
+        if ((r = alloc_mat(e, e->w2[l], (uint32_t)E, (uint32_t)F))) return r;
+        if ((r = put_rows(e, e->w2[l], src_w[5][l], src_a[5][l], (uint32_t)E, 0, 1, staging))) return r;
+    }
+    if ((r = alloc_mat(e, e->emb, (uint32_t)V, (uint32_t)E))) return r;
+    if ((r = put_rows(e, e->emb, emb_w, emb_a, (uint32_t)V, 0, 1, staging))) return r;
+    if (cls_w) {
+        if ((r = alloc_mat(e, e->cls, (uint32_t)V, (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->cls, cls_w, cls_a, (uint32_t)V, 0, 1, staging))) return r;
+    } else {
+        e->cls = e->emb;
+    }
+
+    // ---- activations, KV cache, workspaces ----
+    const size_t kv_floats = (size_t)L * d.KV * d.max_seq * d.hd;
+    DM(e->x, E * 4); DM(e->q, QD * 4); DM(e->kraw, KD * 4); DM(e->xba, QD * 4); DM(e->hb, F * 4); DM(e->logits, V * 4);
+    DM(e->kc, kv_floats * 4); DM(e->vc, kv_floats * 4);
+    CK(cudaMemset(e->kc, 0, kv_floats * 4)); CK(cudaMemset(e->vc, 0, kv_floats * 4));   // calloc'd in the reference (infer.c:47)
+    CK(cudaMemset(e->x, 0, E * 4)); CK(cudaMemset(e->logits, 0, V * 4));
+    uint32_t nsm = (uint32_t)(2 * e->num_sms + d.KV - 1) / d.KV;
+    if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
+    e->nsplit_max = nsm;
+    uint32_t cap = (d.max_seq + nsm - 1) / nsm; cap = (cap + 7u) & ~7u; if (cap < 32) cap = 32;
+    e->chunk_cap = cap;
+    uint32_t lpr = 1; while (lpr * 4 < d.hd) lpr <<= 1; if (lpr > 32) lpr = 32;
+    const uint32_t rpw = 32 / lpr;
+    e->attn_smem = (uint32_t)((d.kv_mul * d.hd + d.hd + cap + (size_t)kAttnWarps * rpw * d.hd) * 4);
+    DM(e->ws_m, (size_t)d.H * nsm * 4); DM(e->ws_l, (size_t)d.H * nsm * 4); DM(e->ws_acc, (size_t)d.H * nsm * d.hd * 4);
+    DM(e->tickets, d.KV * 4); CK(cudaMemset(e->tickets, 0, d.KV * 4));
+    if (d.exact) DM(e->att_exact, (size_t)d.H * d.max_seq * 4);
+    DM(e->ids_dev, ((size_t)d.max_seq + 8) * 4); CK(cudaMemset(e->ids_dev, 0, ((size_t)d.max_seq + 8) * 4));
+    DM(e->seen, V); CK(cudaMemset(e->seen, 0, V));
+    e->cls_grid = (uint32_t)e->num_sms * grid_mult();
+    DM(e->cls_val, (size_t)e->cls_grid * 4); DM(e->cls_idx, (size_t)e->cls_grid * 4);
+    DM(e->st, sizeof(DevState)); CK(cudaMemset(e->st, 0, sizeof(DevState)));
+    const size_t maxn = F > QD ? (F > E ? F : E) : (QD > E ? QD : E);
+    DM(e->dump_codes, maxn * 2 + 64); DM(e->dump_scales, maxn * 4 + 64);
+    CK(cudaHostAlloc(&e->st_host, sizeof(DevState), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&e->tok_host, 64, cudaHostAllocDefault));
+    memset(e->st_host, 0, sizeof(DevState));
+    CK(cudaDeviceSynchronize());
+
+    if (!(flags & NB200_FLAG_NO_GRAPH)) {
+        r = capture_graph(e);
+        if (r && e->use_pdl) {          // retry without PDL edges before giving up on the graph
+            e->use_pdl = false;
+            r = capture_graph(e);
+        }
+        if (r) return r;
+    } else {
+        e->launches_per_token = 2 + 5 * d.L;
+    }
+    guard.ok = true;
+    *out = e;
+    return 0;
+}
+
+int nb200_get_config(const nb200_engine *e, nb200_config *c) {
+    if (!e || !c) return fail(NB200_EINVAL, "null argument");
+    memset(c, 0, sizeof *c);
+    const Dims &d = e->d;
+    c->arch = d.arch; c->quant = d.quant; c->group_size = (d.quant == 0x80u) ? d.gs : 0;
+    c->block_size = d.block_size; c->vocab_size = d.V; c->n_layer = d.L; c->n_embd = d.E; c->n_head = d.H;
+    c->n_kv_head = d.KV; c->n_hidden = d.F; c->tied = (e->cls.w == e->emb.w); c->head_dim = d.hd;
+    c->q_dim = d.q_dim; c->kv_dim = d.kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
+    return 0;
+}
+
+static int push_state(nb200_engine *e, uint32_t pos, uint32_t causal, uint32_t n_prompt, uint32_t advance, float penalty,
+                      uint32_t token, uint32_t use_token) {
+    DevState *h = e->st_host;
+    CK(cudaStreamSynchronize(e->stream));      // the pinned slot may still be in flight
+    memset(h, 0, sizeof(DevState));
+    h->pos = pos; h->is_causal = causal; h->n_prompt = n_prompt; h->advance = advance; h->penalty = penalty;
+    h->token = token; h->use_token = use_token;
+    CK(cudaMemcpyAsync(e->st, h, sizeof(DevState), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+int nb200_forward(nb200_engine *e, uint32_t token, uint32_t pos, uint32_t is_causal) {
+    if (!e) return fail(NB200_EINVAL, "null engine");
+    if (pos >= e->d.max_seq || token >= e->d.V) return fail(NB200_EINVAL, "token/pos out of range");
+    CK(cudaSetDevice(e->device));
+    int r;
+    if ((r = push_state(e, pos, is_causal ? 1u : 0u, 0, 0, 1.0f, token, 1))) return r;
+    if ((r = launch_token(e))) return r;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int nb200_read_logits(nb200_engine *e, float *host_logits) {
+    if (!e || !host_logits) return fail(NB200_EINVAL, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(host_logits, e->logits, (size_t)e->d.V * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int sync_seen(nb200_engine *e, const uint32_t *ids, uint32_t pos) {
+    uint32_t have = (uint32_t)e->seen_mirror.size();
+    bool ok = e->seen_valid && have <= pos && (have == 0 || memcmp(e->seen_mirror.data(), ids, (size_t)have * 4) == 0);
+    if (!ok) {
+        CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
+        e->seen_mirror.clear(); have = 0; e->seen_valid = true;
+    }
+    if (pos > have) {
+        for (uint32_t i = have; i < pos; i++) if (ids[i] >= e->d.V) return fail(NB200_EINVAL, "id out of range");
+        CK(cudaMemcpyAsync(e->ids_dev + have, ids + have, (size_t)(pos - have) * 4, cudaMemcpyHostToDevice, e->stream));
+        k_mark_seen<<<1, 256, 0, e->stream>>>(e->seen, e->ids_dev, have, pos);
+        CK(cudaGetLastError());
+        e->launches++;
+        e->seen_mirror.insert(e->seen_mirror.end(), ids + have, ids + pos);
+    }
+    return 0;
+}
+
+int nb200_next_greedy(nb200_engine *e, const uint32_t *ids, uint32_t pos, int is_prefilling, float penalty, uint32_t *next) {
+    if (!e || !ids || !next) return fail(NB200_EINVAL, "null argument");
+    if (pos >= e->d.max_seq || ids[pos] >= e->d.V) return fail(NB200_EINVAL, "token/pos out of range");
+    CK(cudaSetDevice(e->device));
+    int r;
+    if ((r = push_state(e, pos, 1, 0, 0, is_prefilling ? 1.0f : penalty, ids[pos], 1))) return r;
+    if (!is_prefilling && penalty != 1.0f) { if ((r = sync_seen(e, ids, pos))) return r; }
+    if ((r = launch_token(e))) return r;
+    CK(cudaMemcpyAsync(e->tok_host, &e->st->next_token, 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *next = is_prefilling ? ids[pos + 1] : *e->tok_host;
+    return 0;
+}
+
+int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint32_t n_total, float penalty,
+                        float *prefill_ms, float *device_ms) {
+    if (!e || !ids) return fail(NB200_EINVAL, "null argument");
+    if (n_prompt < 1 || n_total < n_prompt || n_total > e->d.max_seq + 1) return fail(NB200_EINVAL, "bad n_prompt/n_total");
+    for (uint32_t i = 0; i < n_prompt; i++) if (ids[i] >= e->d.V) return fail(NB200_EINVAL, "id out of range");
+    CK(cudaSetDevice(e->device));
+    int r;
+    cudaEvent_t ev[3];
+    for (auto &v : ev) CK(cudaEventCreate(&v));
+    if ((r = push_state(e, 0, 1, n_prompt, 1, penalty, 0, 0))) return r;
+    CK(cudaMemcpyAsync(e->ids_dev, ids, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
+    e->seen_valid = false; e->seen_mirror.clear();
+    CK(cudaEventRecord(ev[0], e->stream));
+    for (uint32_t p = 0; p + 1 < n_prompt; p++) if ((r = launch_token(e))) return r;
+    CK(cudaEventRecord(ev[1], e->stream));
+    for (uint32_t p = n_prompt - 1; p + 1 < n_total; p++) if ((r = launch_token(e))) return r;
+    CK(cudaEventRecord(ev[2], e->stream));
+    CK(cudaMemcpyAsync(ids, e->ids_dev, (size_t)n_total * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
+    if (prefill_ms) *prefill_ms = a;
+    if (device_ms) *device_ms = b;
+    for (auto &v : ev) cudaEventDestroy(v);
+    return 0;
+}
+
+int nb200_read_buffer(nb200_engine *e, int field, uint32_t layer, uint32_t pos, float *dst, uint32_t count) {
+    if (!e || !dst) return fail(NB200_EINVAL, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    const Dims &d = e->d;
+    const float *src = nullptr; uint32_t avail = 0;
+    switch (field) {
+        case NB200_F_X: src = e->x; avail = d.E; break;
+        case NB200_F_XBA: src = e->xba; avail = d.q_dim; break;
+        case NB200_F_HB: src = e->hb; avail = d.F; break;
+        case NB200_F_Q: src = e->q; avail = d.q_dim; break;
+        case NB200_F_LOGITS: src = e->logits; avail = d.V; break;
+        case NB200_F_ACT_SCALE: src = e->dump_scales; avail = count; break;
+        case NB200_F_ACT_I8: {
+            CK(cudaMemcpy(dst, e->dump_codes, count, cudaMemcpyDeviceToHost));   // count = bytes here
+            return 0;
+        }
+        case NB200_F_KROW: case NB200_F_VROW: {
+            if (layer >= d.L || pos >= d.max_seq || count != d.kv_dim) return fail(NB200_EINVAL, "bad KV row request");
+            const float *base = (field == NB200_F_KROW ? e->kc : e->vc) + (size_t)layer * d.KV * d.max_seq * d.hd;
+            for (uint32_t h = 0; h < d.KV; h++)
+                CK(cudaMemcpy(dst + (size_t)h * d.hd, base + ((size_t)h * d.max_seq + pos) * d.hd, (size_t)d.hd * 4, cudaMemcpyDeviceToHost));
+            return 0;
+        }
+        default: return fail(NB200_EINVAL, "unknown field %d", field);
+    }
+    if (count > avail) return fail(NB200_EINVAL, "count %u exceeds field size %u", count, avail);
+    CK(cudaMemcpy(dst, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nb200_write_x(nb200_engine *e, const float *x, uint32_t count) {
+    if (!e || !x || count != e->d.E) return fail(NB200_EINVAL, "bad argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(e->x, x, (size_t)count * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int nb200_run_layer(nb200_engine *e, uint32_t layer, uint32_t pos, uint32_t is_causal) {
+    if (!e || layer >= e->d.L || pos >= e->d.max_seq) return fail(NB200_EINVAL, "bad argument");
+    CK(cudaSetDevice(e->device));
+    int r;
+    if ((r = push_state(e, pos, is_causal ? 1u : 0u, 0, 0, 1.0f, 0, 1))) return r;
+    if ((r = run_layer(e, layer))) return r;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+uint64_t nb200_kernel_launches(const nb200_engine *e) { return e ? e->launches : 0; }
+uint32_t nb200_launches_per_token(const nb200_engine *e) { return e ? e->launches_per_token : 0; }
+uint64_t nb200_weight_bytes(const nb200_engine *e) { return e ? e->weight_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// op-level entry points
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t b) { return cudaMalloc(&p, b ? b : 16) == cudaSuccess ? 0 : fail(NB200_ENOMEM, "cudaMalloc failed"); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+int need_device() {
+    if (nb200_device_count() <= 0) return fail(NB200_ENODEV, "no CUDA device: nano_b200 has no CPU path");
+    return 0;
+}
+int op_prep(uint32_t quant, const float *x, const float *gain, uint32_t n, uint32_t gs, uint32_t exact, float *out_f32,
+            int8_t *codes_host, size_t codes_bytes, float *scales_host, size_t scales_count) {
+    int r;
+    if ((r = need_device())) return r;
+    DevBuf dx, dg, dout, dcodes, dscales;
+    if ((r = dx.alloc((size_t)n * 4)) || (r = dg.alloc((size_t)n * 4)) || (r = dout.alloc((size_t)n * 4)) ||
+        (r = dcodes.alloc((size_t)n * 2 + 64)) || (r = dscales.alloc((size_t)n * 4 + 64))) return r;
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (gain) CK(cudaMemcpy(dg.p, gain, (size_t)n * 4, cudaMemcpyHostToDevice));
+    const uint32_t smem = act_smem_bytes(quant, n, gs ? gs : 1, exact && gain);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void *)k_op_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_op_prep<<<1, kThreads, smem>>>(dx.as<float>(), gain ? dg.as<float>() : nullptr, n, gs, quant, exact, dout.as<float>(),
+                                     dcodes.as<int8_t>(), dscales.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    if (out_f32) CK(cudaMemcpy(out_f32, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (codes_host) CK(cudaMemcpy(codes_host, dcodes.p, codes_bytes, cudaMemcpyDeviceToHost));
+    if (scales_host) CK(cudaMemcpy(scales_host, dscales.p, scales_count * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int op_matvec(uint32_t quant, float *out, const float *x, const void *w, size_t wbytes, const void *aux, size_t auxbytes,
+              uint32_t n, uint32_t d_rows, uint32_t gs, uint32_t exact, bool q4k_file_blocks) {
+    int r;
+    if ((r = need_device())) return r;
+    DevBuf dx, dw, da, dout, dstage;
+    if ((r = dx.alloc((size_t)n * 4)) || (r = dout.alloc((size_t)d_rows * 4))) return r;
+    CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+    Mat m; m.rows = d_rows; m.n = n;
+    if (q4k_file_blocks) {
+        const uint64_t nblocks = (uint64_t)d_rows * (n / 256);
+        if ((r = dstage.alloc(nblocks * 160)) || (r = dw.alloc((size_t)d_rows * n / 2 + 64)) || (r = da.alloc(nblocks * 20 + 64))) return r;
+        CK(cudaMemcpy(dstage.p, w, nblocks * 160, cudaMemcpyHostToDevice));
+        k_q4k_split<<<256, 256>>>(dstage.as<uint8_t>(), nblocks, n / 256, dw.as<uint8_t>(), da.as<uint8_t>(), 0, 1);
+        CK(cudaGetLastError());
+    } else {
+        if ((r = dw.alloc(wbytes + 64))) return r;
+        CK(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
+        if (aux) { if ((r = da.alloc(auxbytes + 64))) return r; CK(cudaMemcpy(da.p, aux, auxbytes, cudaMemcpyHostToDevice)); }
+    }
+    m.w = dw.p; m.aux = da.p;
+    MatvecArgs a{};
+    a.d.quant = quant; a.d.gs = gs; a.d.exact = exact; a.d.hd = 4; a.d.max_seq = 1;
+    a.src = dx.as<float>(); a.gain = nullptr; a.out = dout.as<float>();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if ((r = run_matvec(nullptr, EPI_STORE, m, a, false, sms))) return r;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dout.p, (size_t)d_rows * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int nb200_op_rmsnorm(float *out, const float *x, const float *gain, uint32_t n, uint32_t exact) {
+    if (!out || !x || !gain || !n) return fail(NB200_EINVAL, "bad argument");
+    return op_prep(0x00u, x, gain, n, 1, exact, out, nullptr, 0, nullptr, 0);
+}
+
+int nb200_op_q80_quantize(int8_t *codes, float *scales, const float *x, uint32_t n, uint32_t gs) {
+    if (!codes || !scales || !x || !n) return fail(NB200_EINVAL, "bad argument");
+    if ((gs != 32 && gs != 64 && gs != 128 && gs != 256) || n % gs) return fail(NB200_EINVAL, "unsupported group size");
+    return op_prep(0x80u, x, nullptr, n, gs, 0, nullptr, codes, n, scales, n / gs);
+}
+
+int nb200_op_q80_matvec(float *out, const float *x, const int8_t *wc, const float *wscales, uint32_t n, uint32_t d, uint32_t gs) {
+    if (!out || !x || !wc || !wscales || !n || !d) return fail(NB200_EINVAL, "bad argument");
+    if ((gs != 32 && gs != 64 && gs != 128 && gs != 256) || n % gs) return fail(NB200_EINVAL, "unsupported group size");
+    return op_matvec(0x80u, out, x, wc, (size_t)d * n, wscales, (size_t)d * (n / gs) * 4, n, d, gs, 0, false);
+}
+
+int nb200_op_f32_matvec(float *out, const float *x, const float *w, uint32_t n, uint32_t d, uint32_t exact) {
+    if (!out || !x || !w || !n || !d || n % 4) return fail(NB200_EINVAL, "bad argument (n %% 4 != 0?)");
+    return op_matvec(0x00u, out, x, w, (size_t)d * n * 4, nullptr, 0, n, d, 1, exact, false);
+}
+
+int nb200_op_q4k_quantize(uint8_t *blocks, const float *x, uint32_t n) {
+    if (!blocks || !x || !n || n % 256) return fail(NB200_EINVAL, "bad argument (n %% 256 != 0?)");
+    std::vector<int8_t> codes((size_t)n + 2 * (n / 32));
+    std::vector<float> sc(2 * (size_t)(n / 256));
+    int r = op_prep(0x42u, x, nullptr, n, 32, 0, nullptr, codes.data(), codes.size(), sc.data(), sc.size());
+    if (r) return r;
+    const uint32_t nb = n / 256;
+    memset(blocks, 0, (size_t)nb * 160);
+    for (uint32_t b = 0; b < nb; b++) {          // re-pack into the file block layout (tensor.c:198-241)
+        uint8_t *blk = blocks + (size_t)b * 160;
+        const uint32_t tag = 0x42u, len = 256u;
+        memcpy(blk, &tag, 4); memcpy(blk + 4, &len, 4);
+        memcpy(blk + 12, &sc[b], 4); memcpy(blk + 16, &sc[nb + b], 4);
+        const int8_t *s6 = codes.data() + n + b * 8, *b6 = codes.data() + n + n / 32 + b * 8;
+        for (int g = 0; g < 4; g++) {
+            blk[20 + g] = (uint8_t)(((s6[4 + g] & 0x30) << 2) | (s6[g] & 0x3f));
+            blk[24 + g] = (uint8_t)(((b6[4 + g] & 0x30) << 2) | (b6[g] & 0x3f));
+            blk[28 + g] = (uint8_t)(((b6[4 + g] & 0x0f) << 4) | (s6[4 + g] & 0x0f));
+        }
+        for (uint32_t i = 0; i < 256; i += 2)
+            blk[32 + (i >> 1)] = (uint8_t)((codes[(size_t)b * 256 + i] & 0x0f) | (codes[(size_t)b * 256 + i + 1] << 4));
+    }
+    return 0;
+}
+
+int nb200_op_q4k_matvec(float *out, const float *x, const uint8_t *w_blocks, uint32_t n, uint32_t d) {
+    if (!out || !x || !w_blocks || !n || !d || n % 256) return fail(NB200_EINVAL, "bad argument (n %% 256 != 0?)");
+    return op_matvec(0x42u, out, x, w_blocks, 0, nullptr, 0, n, d, 32, 0, true);
+}
+
+// host-side evaluation of the exact-mode expf (no GPU needed): lets CPU tests pin it to libm
+float nb200_host_expf_ref(float x) { return nb::expf_ref_impl(x); }
+void nb200_host_expf_ref_array(float *dst, const float *src, uint64_t n) { for (uint64_t i = 0; i < n; i++) dst[i] = nb::expf_ref_impl(src[i]); }
+
+}  // extern "C"

@@ -1,0 +1,958 @@
+// kernels.cuh -- sm_100a device code of the batch-1 decode engine.
+//
+// Everything on the per-token path of the reference (infer/infer.c:584-1018, infer/tensor.c) is here:
+//   activation prep ....... rmsnorm (infer.c:601) + Q80 quantize (tensor.c:21) / Q4K quantize (tensor.c:144)
+//   matvec ................ matmul (infer.c:637), matmul_quant (infer.c:654), matmul_q4k (tensor.c:438)
+//   attention ............. q/k head-norm + RoPE (infer.c:814-835), GQA attention (infer.c:841-879)
+//   epilogues ............. KV-cache store, residual add (infer.c:906,963), SwiGLU (infer.c:937),
+//                           repetition penalty + argmax (infer.c:1156-1171, 1026-1037)
+//
+// Numerics contract (DESIGN.md "Numerics"):
+//   * integer work (Q80 / Q4K group dots, activation codes) is exact;
+//   * every fp32 combine that follows an integer dot is evaluated in the reference's order with
+//     __fmul_rn/__fadd_rn (no FMA contraction), so a quantised matvec is bit-identical to the strict
+//     reference given the same activation vector;
+//   * the remaining fp32 reductions (rmsnorm sum, attention, F32 matvec) use parallel trees in fast
+//     mode and the reference's sequential order in exact mode.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "expf_ref.cuh"
+
+namespace nb {
+
+constexpr int kThreads = 512;            // matvec CTA: 16 warps
+constexpr int kWarps = kThreads / 32;
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+constexpr float kTrueMin = 1.401298464324817e-45f;   // FLT_TRUE_MIN (tensor.c:159 quirk)
+
+struct Dims {
+    uint32_t arch, quant, gs;
+    uint32_t block_size, V, L, E, H, KV, F, hd, q_dim, kv_dim, max_seq, kv_mul;
+    uint32_t exact;
+};
+
+// Per-step state that lives in HBM so one captured graph serves every position.
+struct DevState {
+    uint32_t pos;          // position of the token being consumed (ids[pos])
+    uint32_t is_causal;    // 0 => seq2seq mode, attend all max_seq rows (infer.c:849)
+    uint32_t n_prompt;     // device loop: positions < n_prompt-1 are teacher-forced
+    uint32_t advance;      // 1 => the classifier's last CTA appends the token and bumps pos
+    float penalty;         // repetition penalty (1.0 => identity)
+    uint32_t next_token;   // result of the step
+    uint32_t cls_ticket;   // last-CTA election for the argmax
+    uint32_t token;        // API mode: the token to consume (use_token = 1); device loop reads ids[pos]
+    uint32_t use_token;
+    uint32_t pad[3];
+};
+
+enum Epilogue { EPI_STORE = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_CLS = 4 };
+
+struct MatvecArgs {
+    // weights (device layout, see engine.cu "HBM layout")
+    const void *w;          // Q80: int8 [rows][n]; F32: float [rows][n]; Q4K: nibble plane [rows][n/2]
+    const void *w_aux;      // Q80: float scales [rows][n/gs]; Q4K: side records [rows][n/256][20 B]
+    uint32_t rows, n;
+    // activation source
+    const float *src;       // fp32 vector of length n
+    const float *gain;      // rmsnorm gain or nullptr (plain quantise)
+    // outputs
+    float *out;             // STORE/SWIGLU/CLS: vector; RESID: x (in/out)
+    float *out_k, *out_v;   // QKV: raw k scratch [kv_dim]; V cache base of this layer [KV][max_seq][hd]
+    const DevState *st;
+    DevState *st_rw;        // CLS only
+    // CLS extras
+    const uint8_t *seen;    // [V] 1 if id occurred at positions < pos
+    uint8_t *seen_rw;
+    float *cls_val; uint32_t *cls_idx;   // per-CTA partial argmax
+    uint32_t *ids;          // device copy of output_ids
+    // debug dump of the prepared activation (written by CTA 0 when non-null)
+    int8_t *dump_codes; float *dump_scales;
+    Dims d;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 ldg_stream16(const void *p) {
+    int4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < NT / 32) ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float *red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_max(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < NT / 32) ? red[lane] : -FLT_MAX;
+    t = warp_max(t);
+    __syncthreads();
+    return t;
+}
+// tensor.c:4-9, exact in fp32
+__device__ __forceinline__ int nearest_int_magic(float f) {
+    float t = __fadd_rn(f, 12582912.f);
+    return (__float_as_int(t) & 0x007fffff) - 0x00400000;
+}
+// programmatic dependent launch: let the next kernel start its weight prefetch, then wait for our inputs
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// infer.c:601-614.  fast: tree sum; exact: the reference's sequential sum (thread 0 over a smem copy).
+template <int NT>
+__device__ __forceinline__ float rms_inverse(const float *__restrict__ x, int n, bool exact, float *red, float *scratch) {
+    float ss;
+    if (!exact) {
+        float acc = 0.0f;
+        for (int i = threadIdx.x; i < n; i += NT) { float v = x[i]; acc = fmaf(v, v, acc); }
+        ss = block_sum<NT>(acc, red);
+    } else {
+        for (int i = threadIdx.x; i < n; i += NT) scratch[i] = x[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float acc = 0.0f;
+            for (int i = 0; i < n; i++) acc = __fadd_rn(acc, __fmul_rn(scratch[i], scratch[i]));
+            red[0] = acc;
+        }
+        __syncthreads();
+        ss = red[0];
+        __syncthreads();
+    }
+    ss = __fdiv_rn(ss, (float)n);
+    ss = __fadd_rn(ss, 1e-5f);
+    return __fdiv_rn(1.0f, __fsqrt_rn(ss));
+}
+
+__device__ __forceinline__ float act_value(const float *__restrict__ src, const float *__restrict__ gain, float inv, int i) {
+    float v = src[i];
+    return gain ? __fmul_rn(gain[i], __fmul_rn(inv, v)) : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Activation preparation into shared memory (each CTA redoes it: <= 39 KB of L2 reads, no grid sync)
+// smem layouts:
+//   F32 : float v[n]
+//   Q80 : int8 codes[n] | pad16 | float scales[n/gs]
+//   Q4K : u32 xe[n/8] (even elements) | u32 xo[n/8] (odd elements) | float4 {sq,bq,sum_q,0}[n/32]
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, uint32_t gs, bool exact_norm) {
+    uint32_t b;
+    if (quant == 0x00u) b = n * 4u;
+    else if (quant == 0x80u) b = ((n + 15u) & ~15u) + (n / gs) * 4u + 16u;
+    else b = n + (n / 32u) * 16u;
+    if (exact_norm && b < n * 4u) b = n * 4u;     // exact rmsnorm stages x as fp32 before quantising
+    return (b + 15u) & ~15u;
+}
+
+template <int NT>
+__device__ void prep_f32(const float *__restrict__ src, const float *__restrict__ gain, int n, bool exact,
+                         float *act, float *red) {
+    float inv = 1.0f;
+    if (gain) inv = rms_inverse<NT>(src, n, exact, red, act);
+    for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(src, gain, inv, i);
+    __syncthreads();
+}
+
+// tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
+template <int NT>
+__device__ void prep_q80(const float *__restrict__ src, const float *__restrict__ gain, int n, int gs, bool exact,
+                         unsigned char *act, float *red, int8_t *dump_codes, float *dump_scales) {
+    int8_t *codes = reinterpret_cast<int8_t *>(act);
+    float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
+    float inv = 1.0f;
+    if (gain) inv = rms_inverse<NT>(src, n, exact, red, reinterpret_cast<float *>(act));
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = n / gs, epl = gs / 32;      // elements per lane (gs in {32,64,128,256})
+    for (int g = warp; g < G; g += NT / 32) {
+        float v[8];
+        float amax = 0.0f;
+        const int base = g * gs + lane * epl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j < epl) { v[j] = act_value(src, gain, inv, base + j); amax = fmaxf(amax, fabsf(v[j])); }
+        }
+        amax = warp_max(amax);
+        const float sc = __fdiv_rn(amax, 127.0f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j < epl) {
+                int c = (sc == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v[j], sc));
+                codes[base + j] = (int8_t)c;
+            }
+        }
+        if (lane == 0) scales[g] = sc;
+    }
+    __syncthreads();
+    if (dump_codes && blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < n; i += NT) dump_codes[i] = codes[i];
+        for (int i = threadIdx.x; i < G; i += NT) dump_scales[i] = scales[i];
+    }
+}
+
+// tensor.c:144-242 on 256-element blocks (n % 256 == 0); one warp per block, 8 elements per lane.
+// dump (optional, CTA 0): codes[n] as bytes, then per group {s6,b6} and per block {ss,sbias} in dump_scales:
+//   dump_scales[0..n/256)      = ss
+//   dump_scales[n/256..2n/256) = sbias
+//   dump_codes[n .. n + n/32)  = s6, dump_codes[n + n/32 .. n + 2n/32) = b6
+template <int NT>
+__device__ void prep_q4k(const float *__restrict__ src, const float *__restrict__ gain, int n, bool exact,
+                         unsigned char *act, float *red, int8_t *dump_codes, float *dump_scales) {
+    uint32_t *xe = reinterpret_cast<uint32_t *>(act);
+    uint32_t *xo = reinterpret_cast<uint32_t *>(act + n / 2);
+    float4 *gp = reinterpret_cast<float4 *>(act + n);
+    float inv = 1.0f;
+    if (gain) inv = rms_inverse<NT>(src, n, exact, red, reinterpret_cast<float *>(act));
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NB = n / 256;
+    const bool dump = dump_codes && blockIdx.x == 0;
+    for (int b = warp; b < NB; b += NT / 32) {
+        float v[8];
+        float lo = FLT_MAX, hi = kTrueMin;
+        const int base = b * 256 + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            v[j] = act_value(src, gain, inv, base + j);
+            if (v[j] > hi) hi = v[j];
+            if (v[j] < lo) lo = v[j];
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        }
+        const float s = (lo <= 0.0f) ? __fdiv_rn(__fsub_rn(hi, lo), 15.0f) : __fdiv_rn(hi, 15.0f);
+        const float bias = (lo <= 0.0f) ? -lo : 0.0f;
+        uint32_t c[8];
+        int csum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c[j] = (s == 0.0f) ? 0u : (uint32_t)(nearest_int_magic(__fdiv_rn(__fadd_rn(v[j], bias), s)) & 0x0f);
+            csum += (int)c[j];
+        }
+        csum += __shfl_xor_sync(0xffffffffu, csum, 1);
+        csum += __shfl_xor_sync(0xffffffffu, csum, 2);
+        float smax = fmaxf(kTrueMin, s), bmax = fmaxf(kTrueMin, bias);
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+            smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+            bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+        }
+        const float ss = __fdiv_rn(smax, 63.0f), sbias = __fdiv_rn(bmax, 63.0f);
+        const int s6 = (ss == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(s, ss)) & 0x3f);
+        const int b6 = (sbias == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(bias, sbias)) & 0x3f);
+        xe[b * 32 + lane] = c[0] | (c[2] << 8) | (c[4] << 16) | (c[6] << 24);
+        xo[b * 32 + lane] = c[1] | (c[3] << 8) | (c[5] << 16) | (c[7] << 24);
+        if ((lane & 3) == 0)
+            gp[b * 8 + (lane >> 2)] = make_float4(__fmul_rn((float)s6, ss), __fmul_rn((float)b6, sbias), (float)csum, 0.0f);
+        if (dump) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) dump_codes[base + j] = (int8_t)c[j];
+            if ((lane & 3) == 0) {
+                dump_codes[n + b * 8 + (lane >> 2)] = (int8_t)s6;
+                dump_codes[n + n / 32 + b * 8 + (lane >> 2)] = (int8_t)b6;
+            }
+            if (lane == 0) { dump_scales[b] = ss; dump_scales[NB + b] = sbias; }
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-block dot products.  A warp owns RB consecutive rows; lanes split K in 16-byte chunks
+// (one 512-byte step per warp-wide load).  All variants return the row values replicated in
+// every lane.
+// ------------------------------------------------------------------------------------------------
+
+// matmul_quant, infer.c:654-679.  LPG = lanes per quantisation group = gs/16.
+template <int RB, int LPG>
+__device__ __forceinline__ void rows_q80(const int8_t *__restrict__ W, const float *__restrict__ S, uint32_t row0,
+                                         uint32_t rows, uint32_t n, const unsigned char *act, float *val) {
+    constexpr uint32_t gs = LPG * 16;
+    const int lane = threadIdx.x & 31;
+    const int8_t *codes = reinterpret_cast<const int8_t *>(act);
+    const float *xs = reinterpret_cast<const float *>(act + ((n + 15) & ~15));
+    const uint32_t G = n / gs;
+    constexpr int GPS = 32 / LPG;   // groups covered by one 512-byte step
+#pragma unroll
+    for (int r = 0; r < RB; r++) val[r] = 0.0f;
+    for (uint32_t k0 = 0; k0 < n; k0 += 1024) {
+        // ---- issue all loads of two steps first (memory-level parallelism) ----
+        int4 w[2][RB];
+        float ws[2][RB];
+        int4 xq[2];
+        float xsc[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const uint32_t k = k0 + s * 512 + lane * 16;
+            const bool on = k < n;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const uint32_t row = min(row0 + r, rows - 1);
+                w[s][r] = on ? ldg_stream16(W + (size_t)row * n + k) : make_int4(0, 0, 0, 0);
+                ws[s][r] = on ? __ldg(S + (size_t)row * G + k / gs) : 0.0f;
+            }
+            xq[s] = on ? *reinterpret_cast<const int4 *>(codes + k) : make_int4(0, 0, 0, 0);
+            xsc[s] = on ? xs[k / gs] : 0.0f;
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const uint32_t kbase = k0 + s * 512;
+            if (kbase >= n) break;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                int isum = __dp4a(w[s][r].x, xq[s].x, 0);
+                isum = __dp4a(w[s][r].y, xq[s].y, isum);
+                isum = __dp4a(w[s][r].z, xq[s].z, isum);
+                isum = __dp4a(w[s][r].w, xq[s].w, isum);
+#pragma unroll
+                for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+                const float term = __fmul_rn(__fmul_rn((float)isum, ws[s][r]), xsc[s]);
+#pragma unroll
+                for (int g = 0; g < GPS; g++) {
+                    const float t = __shfl_sync(0xffffffffu, term, g * LPG);
+                    if (kbase + g * gs < n) val[r] = __fadd_rn(val[r], t);
+                }
+            }
+        }
+    }
+}
+
+// matmul, infer.c:637-651 (fast mode: lane-split FMA + tree; exact mode uses k_matvec_f32_exact)
+template <int RB>
+__device__ __forceinline__ void rows_f32(const float *__restrict__ W, uint32_t row0, uint32_t rows, uint32_t n,
+                                         const unsigned char *act, float *val) {
+    const int lane = threadIdx.x & 31;
+    const float *x = reinterpret_cast<const float *>(act);
+    float acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) acc[r] = 0.0f;
+    for (uint32_t k0 = 0; k0 < n; k0 += 256) {
+        int4 w[2][RB];
+        float4 xv[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const uint32_t k = k0 + s * 128 + lane * 4;
+            const bool on = k < n;
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const uint32_t row = min(row0 + r, rows - 1);
+                w[s][r] = on ? ldg_stream16(W + (size_t)row * n + k) : make_int4(0, 0, 0, 0);
+            }
+            xv[s] = on ? *reinterpret_cast<const float4 *>(x + k) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                acc[r] = fmaf(__int_as_float(w[s][r].x), xv[s].x, acc[r]);
+                acc[r] = fmaf(__int_as_float(w[s][r].y), xv[s].y, acc[r]);
+                acc[r] = fmaf(__int_as_float(w[s][r].z), xv[s].z, acc[r]);
+                acc[r] = fmaf(__int_as_float(w[s][r].w), xv[s].w, acc[r]);
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) val[r] = warp_sum(acc[r]);
+}
+
+// matmul_q4k / dot_two_blocks_q4k, tensor.c:359-471.  One lane owns one 32-element group per step
+// (16 bytes of nibbles); 8 lanes = one 256-element block.  side: 20-byte records {ss, sbias, sb[12]}.
+template <int RB>
+__device__ __forceinline__ void rows_q4k(const uint8_t *__restrict__ W, const uint8_t *__restrict__ side, uint32_t row0,
+                                         uint32_t rows, uint32_t n, const unsigned char *act, float *val) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t *xe = reinterpret_cast<const uint32_t *>(act);
+    const uint32_t *xo = reinterpret_cast<const uint32_t *>(act + n / 2);
+    const float4 *gp = reinterpret_cast<const float4 *>(act + n);
+    const uint32_t rowbytes = n / 2, bpr = n / 256;
+#pragma unroll
+    for (int r = 0; r < RB; r++) val[r] = 0.0f;
+    for (uint32_t k0 = 0; k0 < rowbytes; k0 += 512) {
+        const uint32_t k = k0 + lane * 16;            // byte offset in the nibble row
+        const bool on = k < rowbytes;
+        const uint32_t grp = k / 16;                  // group index within the row
+        const uint32_t blk = grp >> 3, gi = grp & 7, j = gi & 3;
+        int4 w[RB];
+        uint32_t sb0[RB], sb1[RB], sb2[RB];
+        float ssc[RB], sbi[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const uint32_t row = min(row0 + r, rows - 1);
+            w[r] = on ? ldg_stream16(W + (size_t)row * rowbytes + k) : make_int4(0, 0, 0, 0);
+            const uint32_t *rec = reinterpret_cast<const uint32_t *>(side + ((size_t)row * bpr + (on ? blk : 0)) * 20);
+            ssc[r] = __uint_as_float(__ldg(rec + 0));
+            sbi[r] = __uint_as_float(__ldg(rec + 1));
+            sb0[r] = __ldg(rec + 2); sb1[r] = __ldg(rec + 3); sb2[r] = __ldg(rec + 4);
+        }
+        int4 e4 = make_int4(0, 0, 0, 0), o4 = make_int4(0, 0, 0, 0);
+        float4 q = make_float4(0, 0, 0, 0);
+        if (on) {
+            e4 = *reinterpret_cast<const int4 *>(xe + grp * 4);
+            o4 = *reinterpret_cast<const int4 *>(xo + grp * 4);
+            q = gp[grp];
+        }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const uint32_t bs = (sb0[r] >> (8 * j)) & 0xff, bb = (sb1[r] >> (8 * j)) & 0xff, bh = (sb2[r] >> (8 * j)) & 0xff;
+            const uint32_t s6 = (gi < 4) ? (bs & 0x3f) : ((((bs >> 6) << 4) | (bh & 0x0f)) & 0x3f);
+            const uint32_t b6 = (gi < 4) ? (bb & 0x3f) : ((((bb >> 6) << 4) | (bh >> 4)) & 0x3f);
+            const float sp = __fmul_rn((float)s6, ssc[r]), bp = __fmul_rn((float)b6, sbi[r]);
+            int spq = 0, spp = 0;
+            const int wv[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
+            const int ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            const int ov[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int lo = wv[t] & 0x0f0f0f0f, hi = (wv[t] >> 4) & 0x0f0f0f0f;
+                spq = __dp4a(lo, ev[t], spq); spq = __dp4a(hi, ov[t], spq);
+                spp = __dp4a(lo, 0x01010101, spp); spp = __dp4a(hi, 0x01010101, spp);
+            }
+            // tensor.c:425-428, left to right
+            float term = __fmul_rn(__fmul_rn(sp, q.x), (float)spq);
+            term = __fsub_rn(term, __fmul_rn(__fmul_rn(sp, q.y), (float)spp));
+            term = __fsub_rn(term, __fmul_rn(__fmul_rn(q.x, bp), q.z));
+            term = __fadd_rn(term, __fmul_rn(__fmul_rn(32.0f, bp), q.y));
+            // per-block sequential sum over its 8 groups (lanes 8b..8b+7), then blocks in order
+            float dot = 0.0f;
+            const int lead = lane & ~7;
+#pragma unroll
+            for (int g = 0; g < 8; g++) dot = __fadd_rn(dot, __shfl_sync(0xffffffffu, term, lead + g));
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const float t = __shfl_sync(0xffffffffu, dot, b * 8);
+                if (k0 + b * 128 < rowbytes) val[r] = __fadd_rn(val[r], t);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused matvec kernel: [PDL prologue] -> activation prep -> row blocks -> epilogue
+// ------------------------------------------------------------------------------------------------
+template <int QUANT, int EPI, int RB, int LPG>
+__global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
+    extern __shared__ __align__(16) unsigned char act[];
+    __shared__ float red[32];
+    __shared__ float best_v[kWarps];
+    __shared__ uint32_t best_i[kWarps];
+    __shared__ uint32_t is_last;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const Dims &d = a.d;
+    const bool exact = d.exact != 0;
+    if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), red);
+    else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, d.gs, exact, act, red, a.dump_codes, a.dump_scales);
+    else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, red, a.dump_codes, a.dump_scales);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblocks = (a.rows + RB - 1) / RB;
+    const uint32_t gwarp = blockIdx.x * kWarps + warp, nwarps = gridDim.x * kWarps;
+    const uint32_t pos = a.st ? a.st->pos : 0;
+
+    float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
+    float pen = 1.0f;
+    if (EPI == EPI_CLS) pen = a.st->penalty;
+
+    for (uint32_t rb = gwarp; rb < nblocks; rb += nwarps) {
+        const uint32_t row0 = rb * RB;
+        float val[RB];
+        if (QUANT == 0x00) rows_f32<RB>(static_cast<const float *>(a.w), row0, a.rows, a.n, act, val);
+        else if (QUANT == 0x80) rows_q80<RB, LPG>(static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, act, val);
+        else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
+
+        if (EPI == EPI_SWIGLU) {
+            // rows (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
+#pragma unroll
+            for (int r = 0; r + 1 < RB; r += 2) {
+                const uint32_t row = row0 + r;
+                if (lane == 0 && row + 1 < a.rows) {
+                    const float v1 = val[r], v3 = val[r + 1];
+                    const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, exact ? expf_ref(-v1) : expf(-v1)));
+                    a.out[row >> 1] = __fmul_rn(__fmul_rn(v1, sg), v3);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                const uint32_t row = row0 + r;
+                if (row >= a.rows) break;
+                float v = val[r];
+                if (EPI == EPI_STORE) { if (lane == 0) a.out[row] = v; }
+                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(a.out[row], v); }
+                else if (EPI == EPI_QKV) {
+                    if (lane == 0) {
+                        if (row < d.q_dim) a.out[row] = v;
+                        else if (row < d.q_dim + d.kv_dim) a.out_k[row - d.q_dim] = v;
+                        else {
+                            const uint32_t c = row - d.q_dim - d.kv_dim, h = c / d.hd, i = c % d.hd;
+                            a.out_v[((size_t)h * d.max_seq + pos) * d.hd + i] = v;
+                        }
+                    }
+                } else if (EPI == EPI_CLS) {
+                    // infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037
+                    if (a.seen[row]) v = __fdiv_rn(v, pen);
+                    if (lane == 0) a.out[row] = v;
+                    if (v > bestv) { bestv = v; besti = row; }
+                }
+            }
+        }
+    }
+
+    if (EPI == EPI_CLS) {
+        // rows were visited in ascending order per warp, so (bestv,besti) already holds the first max
+        if (lane == 0) { best_v[warp] = bestv; best_i[warp] = besti; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bv = best_v[0]; uint32_t bi = best_i[0];
+            for (int w = 1; w < kWarps; w++)
+                if (best_v[w] > bv || (best_v[w] == bv && best_i[w] < bi)) { bv = best_v[w]; bi = best_i[w]; }
+            a.cls_val[blockIdx.x] = bv; a.cls_idx[blockIdx.x] = bi;
+            __threadfence();
+            const uint32_t t = atomicAdd(&a.st_rw->cls_ticket, 1u);
+            is_last = (t == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (is_last && threadIdx.x == 0) {
+            __threadfence();
+            float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
+            for (uint32_t c = 0; c < gridDim.x; c++) {
+                const float v = __ldcg(a.cls_val + c); const uint32_t i = __ldcg(a.cls_idx + c);
+                if (i == 0xffffffffu) continue;
+                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+            }
+            if (bi == 0xffffffffu) bi = 0;     // all-NaN row: the reference's argmax returns index 0
+            DevState *st = a.st_rw;
+            st->cls_ticket = 0;
+            const uint32_t p = st->pos;
+            if (st->advance) {
+                const uint32_t tok_in = a.ids[p];
+                a.seen_rw[tok_in] = 1;                          // ids[0..p] are "seen" for step p+1
+                const bool forced = (p + 1 < st->n_prompt);    // infer.c:1250 is_prefilling
+                if (!forced) a.ids[p + 1] = bi;
+                st->next_token = forced ? a.ids[p + 1] : bi;
+                st->pos = p + 1;
+            } else {
+                st->next_token = bi;
+            }
+        }
+    }
+}
+
+// exact-mode F32 matvec: one thread per row, the reference's left-to-right sum (infer.c:645-649)
+template <int EPI>
+__global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
+    extern __shared__ __align__(16) unsigned char act[];
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    prep_f32<256>(a.src, a.gain, a.n, true, reinterpret_cast<float *>(act), red);
+    const float *x = reinterpret_cast<const float *>(act);
+    const float *W = static_cast<const float *>(a.w);
+    const Dims &d = a.d;
+    const uint32_t pos = a.st ? a.st->pos : 0;
+    const uint32_t nunits = (EPI == EPI_SWIGLU) ? a.rows / 2 : a.rows;
+    for (uint32_t u = blockIdx.x * 256 + threadIdx.x; u < nunits; u += gridDim.x * 256) {
+        const int per = (EPI == EPI_SWIGLU) ? 2 : 1;
+        float res[2] = {0.0f, 0.0f};
+        for (int p = 0; p < per; p++) {
+            const float *wr = W + (size_t)(u * per + p) * a.n;
+            float acc = 0.0f;
+            for (uint32_t j = 0; j < a.n; j++) acc = __fadd_rn(acc, __fmul_rn(wr[j], x[j]));
+            res[p] = acc;
+        }
+        const uint32_t row = u;
+        if (EPI == EPI_SWIGLU) {
+            const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_ref(-res[0])));
+            a.out[row] = __fmul_rn(__fmul_rn(res[0], sg), res[1]);
+        } else if (EPI == EPI_STORE) a.out[row] = res[0];
+        else if (EPI == EPI_RESID) a.out[row] = __fadd_rn(a.out[row], res[0]);
+        else if (EPI == EPI_QKV) {
+            if (row < d.q_dim) a.out[row] = res[0];
+            else if (row < d.q_dim + d.kv_dim) a.out_k[row - d.q_dim] = res[0];
+            else {
+                const uint32_t c = row - d.q_dim - d.kv_dim, h = c / d.hd, i = c % d.hd;
+                a.out_v[((size_t)h * d.max_seq + pos) * d.hd + i] = res[0];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding row fetch (infer.c:987-988 with the load-time dequantisation of :126-127 / :147-149)
+// ------------------------------------------------------------------------------------------------
+struct EmbedArgs {
+    const void *w; const void *w_aux;   // same layouts as MatvecArgs (classifier/embedding table)
+    float *x; const uint32_t *ids; const DevState *st; Dims d;
+};
+
+__global__ void __launch_bounds__(256) k_embed(const EmbedArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const Dims &d = a.d;
+    const uint32_t tok = a.st->use_token ? a.st->token : a.ids[a.st->pos];
+    const uint32_t E = d.E;
+    for (uint32_t i = threadIdx.x; i < E; i += 256) {
+        float v;
+        if (d.quant == 0x00u) v = static_cast<const float *>(a.w)[(size_t)tok * E + i];
+        else if (d.quant == 0x80u) {
+            const int8_t c = static_cast<const int8_t *>(a.w)[(size_t)tok * E + i];
+            const float s = static_cast<const float *>(a.w_aux)[((size_t)tok * E + i) / d.gs];
+            v = __fmul_rn((float)c, s);                                  // tensor.c:15-19
+        } else {
+            const uint32_t bpr = E / 256, blk = i >> 8, e = i & 255, g = e >> 5, j = g & 3;
+            const uint8_t byte = static_cast<const uint8_t *>(a.w)[(size_t)tok * (E / 2) + (i >> 1)];
+            const uint32_t c = (i & 1) ? (byte >> 4) : (byte & 0x0f);
+            const uint32_t *rec = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(a.w_aux) + ((size_t)tok * bpr + blk) * 20);
+            const float ss = __uint_as_float(rec[0]), sbi = __uint_as_float(rec[1]);
+            const uint32_t bs = (rec[2] >> (8 * j)) & 0xff, bb = (rec[3] >> (8 * j)) & 0xff, bh = (rec[4] >> (8 * j)) & 0xff;
+            const uint32_t s6 = (g < 4) ? (bs & 0x3f) : ((((bs >> 6) << 4) | (bh & 0x0f)) & 0x3f);
+            const uint32_t b6 = (g < 4) ? (bb & 0x3f) : ((((bb >> 6) << 4) | (bh >> 4)) & 0x3f);
+            v = __fsub_rn(__fmul_rn((float)c, __fmul_rn((float)s6, ss)), __fmul_rn((float)b6, sbi));   // tensor.c:274
+        }
+        a.x[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention (infer.c:814-879): q/k head-norm + RoPE, split-KV partial softmax, last-CTA combine.
+// KV cache layout: [L][KV][max_seq][hd] fp32 (head-major: one split reads one contiguous stream).
+// ------------------------------------------------------------------------------------------------
+struct AttnArgs {
+    const float *q;          // raw q [q_dim]
+    const float *kraw;       // raw k of this position [kv_dim]
+    float *kc, *vc;          // cache bases of this layer [KV][max_seq][hd]
+    const float *qnorm, *knorm;   // Qwen3 gains [hd] of this layer (nullptr otherwise)
+    const float *rope_cos, *rope_sin;   // [block_size][hd/2]
+    float *xba;              // out [q_dim]
+    float *ws_m, *ws_l, *ws_acc;  // partials [H][nsplit_max], [H][nsplit_max], [H][nsplit_max][hd]
+    uint32_t *ticket;        // [KV]
+    const DevState *st;
+    uint32_t nsplit_max, chunk_cap;
+    Dims d;
+};
+
+// one head vector: optional rmsnorm (Qwen3) + rope; in/out in shared memory; called by one warp
+__device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict__ gain, const float *__restrict__ cr,
+                                               const float *__restrict__ ci, const Dims &d, bool exact) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t hd = d.hd;
+    if (d.arch == 3u) {
+        float inv;
+        if (!exact) {
+            float acc = 0.0f;
+            for (uint32_t i = lane; i < hd; i += 32) acc = fmaf(h[i], h[i], acc);
+            acc = warp_sum(acc);
+            inv = acc;
+        } else {
+            float acc = 0.0f;
+            for (uint32_t i = 0; i < hd; i++) acc = __fadd_rn(acc, __fmul_rn(h[i], h[i]));
+            inv = acc;
+        }
+        inv = __fdiv_rn(inv, (float)hd);
+        inv = __fadd_rn(inv, 1e-5f);
+        inv = __fdiv_rn(1.0f, __fsqrt_rn(inv));
+        __syncwarp();
+        for (uint32_t i = lane; i < hd; i += 32) h[i] = __fmul_rn(gain[i], __fmul_rn(inv, h[i]));
+        __syncwarp();
+        const uint32_t half = hd / 2;                  // infer.c:692-706
+        for (uint32_t i = lane; i < half; i += 32) {
+            const float c = cr[i], s = ci[i], v0 = h[i], v1 = h[i + half];
+            h[i] = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
+            h[i + half] = __fadd_rn(__fmul_rn(v1, c), __fmul_rn(v0, s));
+        }
+    } else {                                            // infer.c:681-690
+        for (uint32_t i = 2 * lane; i < hd; i += 64) {
+            const float c = cr[i / 2], s = ci[i / 2], v0 = h[i], v1 = h[i + 1];
+            h[i] = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
+            h[i + 1] = __fadd_rn(__fmul_rn(v0, s), __fmul_rn(v1, c));
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float red[32];
+    __shared__ uint32_t is_last;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const Dims &d = a.d;
+    const bool exact = d.exact != 0;
+    const uint32_t hd = d.hd, kvm = d.kv_mul;
+    const uint32_t g = blockIdx.y, split = blockIdx.x;
+    const uint32_t pos = a.st->pos;
+    const uint32_t range = a.st->is_causal ? pos + 1 : d.max_seq;
+    uint32_t chunk = (range + a.nsplit_max - 1) / a.nsplit_max;
+    chunk = max(chunk, 32u);
+    chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
+    const uint32_t nsplit = (range + chunk - 1) / chunk;
+    if (split >= nsplit) return;
+    const uint32_t t0 = split * chunk, t1 = min(range, t0 + chunk), len = t1 - t0;
+    const bool owner = (pos >= t0 && pos < t1);
+
+    // smem carve-up
+    float *qs = sm;                          // [kvm][hd]
+    float *krow = qs + kvm * hd;             // [hd]
+    float *sc = krow + hd;                   // [chunk_cap]
+    float *part = sc + a.chunk_cap;          // [kAttnWarps * rows_per_warp][hd]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
+
+    for (uint32_t i = threadIdx.x; i < kvm * hd; i += kAttnThreads) qs[i] = a.q[(size_t)g * kvm * hd + i];
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) krow[i] = a.kraw[(size_t)g * hd + i];
+    __syncthreads();
+    for (uint32_t m = warp; m < kvm + (owner ? 1u : 0u); m += kAttnWarps) {
+        if (m < kvm) head_norm_rope(qs + m * hd, a.qnorm, cr, ci, d, exact);
+        else head_norm_rope(krow, a.knorm, cr, ci, d, exact);
+    }
+    __syncthreads();
+    float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) kbase[(size_t)pos * hd + i] = krow[i];
+
+    // lanes per cache row: smallest power of two >= hd/4 (float4 per lane)
+    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1; if (lpr > 32) lpr = 32;
+    const uint32_t rpw = 32 / lpr;                      // rows per warp-iteration
+    const uint32_t sub = lane / lpr, li = lane % lpr;
+    const float inv_div = sqrtf((float)hd);
+
+    for (uint32_t m = 0; m < kvm; m++) {
+        const uint32_t h = g * kvm + m;
+        const float *qh = qs + m * hd;
+        // ---- scores ----
+        for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+            const uint32_t tl = tb + sub;
+            float acc = 0.0f;
+            if (tl < len) {
+                const uint32_t t = t0 + tl;
+                const float *kr = (t == pos) ? krow : kbase + (size_t)t * hd;
+                for (uint32_t c = li * 4; c < hd; c += lpr * 4) {
+                    const float4 kv = *reinterpret_cast<const float4 *>(kr + c);
+                    const float4 qv = *reinterpret_cast<const float4 *>(qh + c);
+                    acc = fmaf(kv.x, qv.x, acc); acc = fmaf(kv.y, qv.y, acc);
+                    acc = fmaf(kv.z, qv.z, acc); acc = fmaf(kv.w, qv.w, acc);
+                }
+            }
+            for (uint32_t o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (tl < len && li == 0) sc[tl] = __fdiv_rn(acc, inv_div);
+        }
+        __syncthreads();
+        // ---- local softmax statistics ----
+        float mx = -FLT_MAX;
+        for (uint32_t t = threadIdx.x; t < len; t += kAttnThreads) mx = fmaxf(mx, sc[t]);
+        mx = block_max<kAttnThreads>(mx, red);
+        float lsum = 0.0f;
+        for (uint32_t t = threadIdx.x; t < len; t += kAttnThreads) { const float e = expf(sc[t] - mx); sc[t] = e; lsum += e; }
+        lsum = block_sum<kAttnThreads>(lsum, red);
+        // ---- weighted V ----
+        float4 av[4];                                   // hd <= 512 : up to 4 float4 per lane at lpr = 32
+#pragma unroll
+        for (int c = 0; c < 4; c++) av[c] = make_float4(0, 0, 0, 0);
+        for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+            const uint32_t tl = tb + sub;
+            if (tl < len) {
+                const float e = sc[tl];
+                const float *vr = vbase + (size_t)(t0 + tl) * hd;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t col = (li + c * lpr) * 4;
+                    if (col < hd) {
+                        const float4 vv = *reinterpret_cast<const float4 *>(vr + col);
+                        av[c].x = fmaf(e, vv.x, av[c].x); av[c].y = fmaf(e, vv.y, av[c].y);
+                        av[c].z = fmaf(e, vv.z, av[c].z); av[c].w = fmaf(e, vv.w, av[c].w);
+                    }
+                }
+            }
+        }
+        float *mypart = part + (size_t)(warp * rpw + sub) * hd;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t col = (li + c * lpr) * 4;
+            if (col < hd) *reinterpret_cast<float4 *>(mypart + col) = av[c];
+        }
+        __syncthreads();
+        const size_t slot = (size_t)h * a.nsplit_max + split;
+        for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) {
+            float s = 0.0f;
+            for (uint32_t p = 0; p < kAttnWarps * rpw; p++) s += part[(size_t)p * hd + i];
+            a.ws_acc[slot * hd + i] = s;
+        }
+        if (threadIdx.x == 0) { a.ws_m[slot] = mx; a.ws_l[slot] = lsum; }
+        __syncthreads();
+    }
+
+    // ---- last CTA of this kv head merges the splits ----
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(a.ticket + g, 1u);
+        is_last = (t == nsplit - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (uint32_t m = 0; m < kvm; m++) {
+        const uint32_t h = g * kvm + m;
+        float M = -FLT_MAX;
+        for (uint32_t s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.ws_m + (size_t)h * a.nsplit_max + s));
+        float Lsum = 0.0f;
+        for (uint32_t s = 0; s < nsplit; s++) {
+            const size_t slot = (size_t)h * a.nsplit_max + s;
+            Lsum += __ldcg(a.ws_l + slot) * expf(__ldcg(a.ws_m + slot) - M);
+        }
+        for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) {
+            float o = 0.0f;
+            for (uint32_t s = 0; s < nsplit; s++) {
+                const size_t slot = (size_t)h * a.nsplit_max + s;
+                o += __ldcg(a.ws_acc + slot * hd + i) * expf(__ldcg(a.ws_m + slot) - M);
+            }
+            a.xba[(size_t)h * hd + i] = __fdiv_rn(o, Lsum);
+        }
+    }
+    if (threadIdx.x == 0) a.ticket[g] = 0;
+}
+
+// exact-mode attention: one CTA per q head, the reference's loop order (infer.c:841-879).
+// att: [H][max_seq] scratch in HBM.
+struct AttnExactArgs {
+    const float *q, *kraw; float *kc, *vc; const float *qnorm, *knorm, *rope_cos, *rope_sin;
+    float *xba; float *att; const DevState *st; Dims d;
+};
+
+__global__ void __launch_bounds__(kAttnThreads) k_attention_exact(const AttnExactArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const Dims &d = a.d;
+    const uint32_t hd = d.hd, h = blockIdx.x, g = h / d.kv_mul;
+    const uint32_t pos = a.st->pos;
+    const uint32_t range = a.st->is_causal ? pos + 1 : d.max_seq;
+    float *qs = sm, *krow = sm + hd;
+    const int warp = threadIdx.x >> 5;
+    const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
+    for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) { qs[i] = a.q[(size_t)h * hd + i]; krow[i] = a.kraw[(size_t)g * hd + i]; }
+    __syncthreads();
+    if (warp == 0) head_norm_rope(qs, a.qnorm, cr, ci, d, true);
+    if (warp == 1) head_norm_rope(krow, a.knorm, cr, ci, d, true);
+    __syncthreads();
+    float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
+    if (h % d.kv_mul == 0) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) kbase[(size_t)pos * hd + i] = krow[i];
+    float *att = a.att + (size_t)h * d.max_seq;
+    const float dv = sqrtf((float)hd);
+    for (uint32_t t = threadIdx.x; t < range; t += kAttnThreads) {
+        const float *kr = (t == pos) ? krow : kbase + (size_t)t * hd;
+        float s = 0.0f;
+        for (uint32_t i = 0; i < hd; i++) s = __fadd_rn(s, __fmul_rn(qs[i], kr[i]));
+        att[t] = __fdiv_rn(s, dv);
+    }
+    __syncthreads();
+    float mx = -FLT_MAX;
+    for (uint32_t t = threadIdx.x; t < range; t += kAttnThreads) mx = fmaxf(mx, att[t]);
+    mx = block_max<kAttnThreads>(mx, red);
+    for (uint32_t t = threadIdx.x; t < range; t += kAttnThreads) att[t] = expf_ref(__fsub_rn(att[t], mx));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (uint32_t t = 0; t < range; t++) s = __fadd_rn(s, att[t]);
+        red[0] = s;
+    }
+    __syncthreads();
+    const float total = red[0];
+    for (uint32_t t = threadIdx.x; t < range; t += kAttnThreads) att[t] = __fdiv_rn(att[t], total);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) {
+        float o = 0.0f;
+        for (uint32_t t = 0; t < range; t++) {
+            const float v = vbase[(size_t)t * hd + i];
+            o = __fadd_rn(o, __fmul_rn(att[t], v));
+        }
+        a.xba[(size_t)h * hd + i] = o;
+    }
+}
+
+// penalty + first-max argmax + state update over logits already in HBM (exact-mode F32 classifier)
+struct FinalizeArgs { float *logits; uint32_t V; const uint8_t *seen; uint8_t *seen_rw; uint32_t *ids; DevState *st; };
+
+__global__ void __launch_bounds__(1024) k_cls_finalize(const FinalizeArgs a) {
+    float *logits = a.logits; const uint32_t V = a.V; const uint8_t *seen = a.seen; uint8_t *seen_rw = a.seen_rw;
+    uint32_t *ids = a.ids; DevState *st = a.st;
+    __shared__ float bvs[32];
+    __shared__ uint32_t bis[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const float pen = st->penalty;
+    float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < V; i += 1024) {
+        float v = logits[i];
+        if (seen[i]) { v = __fdiv_rn(v, pen); logits[i] = v; }
+        if (v > bv) { bv = v; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bvs[threadIdx.x >> 5] = bv; bis[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; w++) if (bvs[w] > bv || (bvs[w] == bv && bis[w] < bi)) { bv = bvs[w]; bi = bis[w]; }
+        if (bi == 0xffffffffu) bi = 0;
+        const uint32_t p = st->pos;
+        if (st->advance) {
+            const uint32_t tok_in = ids[p];
+            seen_rw[tok_in] = 1;
+            const bool forced = (p + 1 < st->n_prompt);
+            if (!forced) ids[p + 1] = bi;
+            st->next_token = forced ? ids[p + 1] : bi;
+            st->pos = p + 1;
+        } else st->next_token = bi;
+    }
+}
+
+// marks seen[ids[i]] for i in [lo, hi) (repetition-penalty bookkeeping in API mode)
+__global__ void k_mark_seen(uint8_t *seen, const uint32_t *ids, uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) seen[ids[i]] = 1;
+}
+
+// standalone prep kernels for the op-level C-ABI (same device functions as the fused prologues)
+__global__ void __launch_bounds__(kThreads) k_op_prep(const float *src, const float *gain, uint32_t n, uint32_t gs, uint32_t quant,
+                                                     uint32_t exact, float *out_f32, int8_t *dump_codes, float *dump_scales) {
+    extern __shared__ __align__(16) unsigned char act[];
+    __shared__ float red[32];
+    if (quant == 0x00u) {
+        prep_f32<kThreads>(src, gain, n, exact != 0, reinterpret_cast<float *>(act), red);
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) out_f32[i] = reinterpret_cast<float *>(act)[i];
+    } else if (quant == 0x80u) prep_q80<kThreads>(src, gain, n, gs, exact != 0, act, red, dump_codes, dump_scales);
+    else prep_q4k<kThreads>(src, gain, n, exact != 0, act, red, dump_codes, dump_scales);
+}
+
+}  // namespace nb

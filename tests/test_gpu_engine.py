@@ -1,0 +1,182 @@
+"""GPU parity tests, engine level: CUDA path (through the C-ABI) vs the oracle on the same seeded files.
+
+Tolerances (BASELINE.json north_star): logits within 1e-4 (FP32) / 1e-2 (Q80, Q4K) in fast mode; exact mode
+(reference-order reductions + glibc-equivalent expf) must be bit-identical to the strict oracle.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_bits_equal
+from nano_b200 import engine as E, modelfile as mf
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+TOY = [("toy-nano", mf.QUANT_F32, 128), ("toy-nano", mf.QUANT_Q80, 64), ("toy-nano", mf.QUANT_Q4K, 128),
+       ("toy-qwen3", mf.QUANT_F32, 128), ("toy-qwen3", mf.QUANT_Q80, 64), ("toy-qwen3", mf.QUANT_Q4K, 128),
+       ("mini-qwen3", mf.QUANT_Q80, 128), ("mini-nano", mf.QUANT_Q80, 128), ("mini-nano", mf.QUANT_Q4K, 128)]
+TOL = {mf.QUANT_F32: 1e-4, mf.QUANT_Q80: 1e-2, mf.QUANT_Q4K: 1e-2}
+
+
+def seq2seq_ids(eng, ids):
+    n = len(ids)
+    for _ in range(eng.n_layer):
+        for p in range(n):
+            eng.forward(ids[p], p, 0)
+    return [int(np.argmax(eng.forward(ids[p], p, 0))) for p in range(n)]
+
+
+def test_sort_model_known_answers(sort_model):
+    """The reference's own fixture (main_sort.c, README.md:379) through the CUDA engine, fast and exact."""
+    kat = json.load(open(os.path.join(GOLDEN, "sort6_kat.json")))
+    for flags in (0, E.FLAG_EXACT):
+        for src, want in kat.items():
+            eng = E.Engine(sort_model, 6, flags=flags)
+            got = seq2seq_ids(eng, [17 + int(c) for c in src])
+            assert "".join(str(t - 17) for t in got) == want, (flags, src, got)
+            eng.close()
+
+
+def test_sort_model_logits_exact_mode(sort_model):
+    eng = E.Engine(sort_model, 6, flags=E.FLAG_EXACT); o = ob.NanoOracle(sort_model, 6)
+    ids = [17 + int(c) for c in "251212"]
+    for _ in range(2):
+        for p in range(6):
+            assert_bits_equal(eng.forward(ids[p], p, 0), o.forward(ids[p], p, 0), f"pos {p}")
+    eng.close(); o.close()
+
+
+@pytest.mark.parametrize("name,quant,gs", TOY)
+def test_teacher_forced_logits_fast_mode(name, quant, gs):
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S = 40
+    eng = E.Engine(path, S); o = ob.NanoOracle(path, S)
+    toks = mf.teacher_tokens(S, spec.vocab)
+    worst, agree = 0.0, 0
+    for pos in range(S):
+        a = eng.forward(toks[pos], pos); b = o.forward(toks[pos], pos)
+        worst = max(worst, float(np.abs(a - b).max()))
+        agree += int(np.argmax(a) == np.argmax(b))
+    assert worst <= TOL[quant], f"{name} {quant:#x}: max|dlogit| {worst}"
+    assert agree >= S - 1
+    eng.close(); o.close()
+
+
+@pytest.mark.parametrize("name,quant,gs", TOY)
+def test_teacher_forced_logits_exact_mode_bit_identical(name, quant, gs):
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S = 24
+    eng = E.Engine(path, S, flags=E.FLAG_EXACT); o = ob.NanoOracle(path, S)
+    toks = mf.teacher_tokens(S, spec.vocab)
+    for pos in range(S):
+        assert_bits_equal(eng.forward(toks[pos], pos), o.forward(toks[pos], pos), f"{name} {quant:#x} pos {pos}")
+    ok, ov = o.kv()
+    for l in range(spec.n_layer):
+        for pos in (0, S - 1):
+            assert_bits_equal(eng.read(E.F_KROW, spec.kv_dim, l, pos), ok[l, pos], "K row")
+            assert_bits_equal(eng.read(E.F_VROW, spec.kv_dim, l, pos), ov[l, pos], "V row")
+    eng.close(); o.close()
+
+
+@pytest.mark.parametrize("name,quant,gs", [("toy-qwen3", mf.QUANT_Q80, 64), ("toy-nano", mf.QUANT_Q4K, 128), ("toy-nano", mf.QUANT_F32, 128)])
+def test_matches_committed_reference_goldens(name, quant, gs):
+    """Exact mode vs logits dumped from the unmodified strict reference (tests/golden/toy_logits.npz)."""
+    spec = mf.PRESETS[name]
+    gold = np.load(os.path.join(GOLDEN, "toy_logits.npz"))[f"{name}_{quant:02x}_{gs}"]
+    eng = E.Engine(mf.cached_model(spec, quant, gs), 24, flags=E.FLAG_EXACT)
+    toks = mf.teacher_tokens(24, spec.vocab)
+    rows = []
+    for pos in range(24):
+        lg = eng.forward(toks[pos], pos)
+        if pos in (0, 1, 7, 23):
+            rows.append(lg)
+    assert_bits_equal(np.stack(rows), gold, name)
+    eng.close()
+
+
+@pytest.mark.parametrize("name,quant,gs", [("toy-qwen3", mf.QUANT_Q80, 64), ("toy-nano", mf.QUANT_Q4K, 128)])
+def test_layer_level_with_injected_inputs(name, quant, gs):
+    """SURVEY 8(d) check 2: oracle x at ATTN_NORM of layer l injected into the GPU layer; outputs compared."""
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S = 12
+    o = ob.NanoOracle(path, S); eng = E.Engine(path, S)
+    toks = mf.teacher_tokens(S, spec.vocab)
+    for pos in range(S):
+        xin = o.probe(1, "ATTN_NORM", "x", spec.n_embd)
+        o.forward(toks[pos], pos); xin = xin.copy()
+        xout = o.probe(spec.n_layer, "FINAL_NORM", "x", spec.n_embd)     # x after the last layer (= layer 1 here)
+        o.forward(toks[pos], pos); xout = xout.copy()
+        eng.forward_nolog(toks[pos], pos)               # fills layer-0 KV rows etc.
+        eng.write_x(xin)
+        eng.run_layer(1, pos)
+        got = eng.read(E.F_X, spec.n_embd)
+        assert np.abs(got - xout).max() <= 2e-3, f"pos {pos}: {np.abs(got - xout).max()}"
+    eng.close(); o.close()
+
+
+@pytest.mark.parametrize("penalty", [1.0, 1.3])
+@pytest.mark.parametrize("name,quant,gs", [("toy-qwen3", mf.QUANT_Q80, 64), ("toy-nano", mf.QUANT_F32, 128), ("mini-nano", mf.QUANT_Q4K, 128)])
+def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty):
+    """generate_next_token semantics (prefill forcing, penalty over ids[0..pos), first-max argmax): ids identical
+    to the oracle in exact mode; the device-resident loop reproduces the per-call API loop."""
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S, P = 40, 6
+    prompt = [5, 9, 5, 3, 9, 5]
+    o = ob.NanoOracle(path, S)
+    ids_o = np.zeros(S + 1, np.uint32); ids_o[:P] = prompt
+    for pos in range(S - 1):
+        ids_o[pos + 1] = o.next_greedy(ids_o, pos, 1 if pos < P - 1 else 0, penalty)
+    for flags in (E.FLAG_EXACT, E.FLAG_EXACT | E.FLAG_NO_GRAPH):
+        eng = E.Engine(path, S, flags=flags)
+        ids = np.zeros(S + 1, np.uint32); ids[:P] = prompt
+        for pos in range(S - 1):
+            ids[pos + 1] = eng.next_greedy(ids, pos, 1 if pos < P - 1 else 0, penalty)
+        assert ids[:S].tolist() == ids_o[:S].tolist()
+        ids2 = np.zeros(S + 1, np.uint32); ids2[:P] = prompt
+        eng.decode_greedy(ids2, P, S, penalty)
+        assert ids2[:S].tolist() == ids_o[:S].tolist()
+        eng.close()
+    # fast mode: device loop == API loop (same kernels, same order)
+    eng = E.Engine(path, S)
+    a = np.zeros(S + 1, np.uint32); a[:P] = prompt
+    for pos in range(S - 1):
+        a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
+    b = np.zeros(S + 1, np.uint32); b[:P] = prompt
+    eng.decode_greedy(b, P, S, penalty)
+    assert a[:S].tolist() == b[:S].tolist()
+    eng.close(); o.close()
+
+
+def test_activation_codes_dump_bit_exact():
+    """The fused prologue's int8 codes (rmsnorm + quantize of layer L-1's QKV input) equal the oracle's in exact mode."""
+    spec = mf.PRESETS["toy-qwen3"]
+    path = mf.cached_model(spec, mf.QUANT_Q80, 64)
+    eng = E.Engine(path, 8, flags=E.FLAG_EXACT); o = ob.NanoOracle(path, 8)
+    xb = o.probe(spec.n_layer - 1, "QKV", "xb", spec.n_embd)
+    o.forward(77, 0); eng.forward_nolog(77, 0)
+    q = np.zeros(spec.n_embd, np.int8); s = np.zeros(spec.n_embd // 64, np.float32)
+    ob.NanoOracle.lib().nor_q80_quantize(q.ctypes.data_as(ob.i8p), s.ctypes.data_as(ob.f32p), xb.ctypes.data_as(ob.f32p), spec.n_embd, 64)
+    got_q = eng.read(E.F_ACT_I8, spec.n_embd, dtype=np.int8)
+    got_s = eng.read(E.F_ACT_SCALE, spec.n_embd // 64)
+    assert_bits_equal(got_q, q, "codes"); assert_bits_equal(got_s, s, "scales")
+    eng.close(); o.close()
+
+
+def test_rejects_bad_inputs():
+    spec = mf.PRESETS["toy-nano"]
+    path = mf.cached_model(spec, mf.QUANT_Q80, 64)
+    eng = E.Engine(path, 8)
+    with pytest.raises(E.NB200Error):
+        eng.forward(spec.vocab, 0)          # token out of range
+    with pytest.raises(E.NB200Error):
+        eng.forward(1, 8)                   # pos >= max_seq_len
+    eng.close()
+    with pytest.raises(E.NB200Error):
+        E.Engine(b"\0" * 4096, 8)           # bad magic
