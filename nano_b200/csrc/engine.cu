@@ -104,6 +104,10 @@ struct nb200_engine {
     bool seen_valid = false;
     std::vector<void *> allocs;
     uint32_t tp_rank = 0, tp_size = 1;
+    // per-kernel-class event profiling (nb200_profile_tokens)
+    bool prof_on = false; int prof_tag = 0;
+    struct ProfRec { int tag; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -129,7 +133,16 @@ int launch(nb200_engine *e, void (*kern)(const Args), dim3 grid, dim3 block, siz
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaLaunchKernelEx(&cfg, kern, args));
+    if (e && e->prof_on) {
+        nb200_engine::ProfRec r{e->prof_tag, nullptr, nullptr};
+        CK(cudaEventCreate(&r.a)); CK(cudaEventCreate(&r.b));
+        CK(cudaEventRecord(r.a, e->stream));
+        CK(cudaLaunchKernelEx(&cfg, kern, args));
+        CK(cudaEventRecord(r.b, e->stream));
+        e->prof.push_back(r);
+    } else {
+        CK(cudaLaunchKernelEx(&cfg, kern, args));
+    }
     if (e) e->launches++;
     return 0;
 }
@@ -211,6 +224,7 @@ MatvecArgs base_args(nb200_engine *e) {
 int run_embed(nb200_engine *e) {
     EmbedArgs a{};
     a.w = e->emb.w; a.w_aux = e->emb.aux; a.x = e->x; a.ids = e->ids_dev; a.st = e->st; a.d = e->d;
+    e->prof_tag = 0;
     return launch<EmbedArgs>(e, k_embed, dim3(1), dim3(256), 0, a);
 }
 
@@ -223,8 +237,10 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.src = e->x; a.gain = e->norm_attn + (size_t)l * d.E;
         a.out = e->q; a.out_k = e->kraw; a.out_v = e->vc + l * kvl;
         a.dump_codes = e->dump_codes; a.dump_scales = e->dump_scales;
+        e->prof_tag = 1;
         if ((r = run_matvec(e, EPI_QKV, e->qkv[l], a, true, e->num_sms))) return r;
     }
+    e->prof_tag = 2;
     if (!d.exact) {   // F2: head-norm + RoPE + split-KV attention
         AttnArgs a{};
         a.q = e->q; a.kraw = e->kraw; a.kc = e->kc + l * kvl; a.vc = e->vc + l * kvl;
@@ -245,22 +261,26 @@ int run_layer(nb200_engine *e, uint32_t l) {
     {   // F3: quantise(xba) + O matvec + residual
         MatvecArgs a = base_args(e);
         a.src = e->xba; a.gain = nullptr; a.out = e->x;
+        e->prof_tag = 3;
         if ((r = run_matvec(e, EPI_RESID, e->wo[l], a, false, e->num_sms))) return r;
     }
     {   // F4: rmsnorm + quantise + W1|W3 matvec + SwiGLU
         MatvecArgs a = base_args(e);
         a.src = e->x; a.gain = e->norm_ffn + (size_t)l * d.E; a.out = e->hb;
+        e->prof_tag = 4;
         if ((r = run_matvec(e, EPI_SWIGLU, e->w13[l], a, true, e->num_sms))) return r;
     }
     {   // F5: quantise(hb) + W2 matvec + residual
         MatvecArgs a = base_args(e);
         a.src = e->hb; a.gain = nullptr; a.out = e->x;
+        e->prof_tag = 5;
         if ((r = run_matvec(e, EPI_RESID, e->w2[l], a, false, e->num_sms))) return r;
     }
     return 0;
 }
 
 int run_classifier(nb200_engine *e) {
+    e->prof_tag = 6;
     MatvecArgs a = base_args(e);
     a.src = e->x; a.gain = e->norm_final; a.out = e->logits;
     if (e->d.quant == 0x00u && e->d.exact) {
@@ -735,6 +755,32 @@ int nb200_run_layer(nb200_engine *e, uint32_t layer, uint32_t pos, uint32_t is_c
     if ((r = run_layer(e, layer))) return r;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
+}
+
+// Runs tokens ids[start..start+n) (teacher-forced, API mode) WITHOUT graph/PDL and with a CUDA-event pair
+// around every kernel; accumulates device milliseconds and launch counts per kernel class:
+// 0 embed, 1 qkv, 2 attention, 3 o-proj, 4 w1|w3, 5 w2, 6 classifier.
+int nb200_profile_tokens(nb200_engine *e, const uint32_t *ids, uint32_t start, uint32_t n, float ms[7], uint32_t counts[7]) {
+    if (!e || !ids || !ms || !counts) return fail(NB200_EINVAL, "null argument");
+    if (start + n > e->d.max_seq) return fail(NB200_EINVAL, "range exceeds max_seq_len");
+    CK(cudaSetDevice(e->device));
+    const bool pdl = e->use_pdl;
+    e->use_pdl = false; e->prof_on = true;
+    int r = 0;
+    for (uint32_t i = 0; i < n && !r; i++) {
+        r = push_state(e, start + i, 1, 0, 0, 1.0f, ids[start + i], 1);
+        if (!r) r = run_token(e);
+    }
+    e->prof_on = false; e->use_pdl = pdl;
+    cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < 7; k++) { ms[k] = 0.0f; counts[k] = 0; }
+    for (auto &p : e->prof) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess && p.tag >= 0 && p.tag < 7) { ms[p.tag] += t; counts[p.tag]++; }
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    e->prof.clear();
+    return r;
 }
 
 uint64_t nb200_kernel_launches(const nb200_engine *e) { return e ? e->launches : 0; }

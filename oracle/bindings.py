@@ -14,6 +14,12 @@ from typing import Optional
 
 import numpy as np
 
+# libgomp reads these once, when the first OpenMP library is loaded into the process.  Parity tests run tiny
+# models: a full-machine team that spin-waits between hundreds of small parallel regions is pathological on
+# the many-core GPU hosts.  bench.py's CPU baselines set their own values in a subprocess.
+os.environ.setdefault("OMP_NUM_THREADS", "8")
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REFERENCE_SRC = "/root/reference/infer"
@@ -97,6 +103,8 @@ class NanoOracle:
             L.nor_q4k_dequant_block.argtypes = [u8p, f32p]
             L.nor_matvec_q4k.argtypes = [f32p, u8p, u8p, C.c_uint64, C.c_uint32, C.c_uint32]
             L.nor_expf_array.argtypes = [f32p, f32p, C.c_uint64]
+            L.nor_set_threads.argtypes = [C.c_int]
+            L.nor_max_threads.restype = C.c_int
             cls._lib = L
         return cls._lib
 

@@ -19,6 +19,7 @@
  */
 #include <float.h>
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -46,6 +47,13 @@ static inline void wr_f32(uint8_t *p, float v) { memcpy(p, &v, 4); }
 /* Elementary ops                                                                              */
 /* ------------------------------------------------------------------------------------------ */
 
+/* OpenMP team size for the row-parallel loops (the reference leaves it to OMP_NUM_THREADS). Tiny loops
+ * stay serial: forking a 200-thread team per 256-row matvec dominates on many-core hosts. */
+static int g_threads = 8;
+void nor_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+int nor_max_threads(void) { return omp_get_num_procs(); }
+#define NOR_PAR(work) num_threads(g_threads) if ((work) >= (1 << 18))
+
 /* infer.c:601-614 */
 void nor_rmsnorm(float *out, const float *x, const float *gain, int n) {
     float acc = 0.0f;
@@ -67,7 +75,7 @@ void nor_softmax(float *v, int n) {
 
 /* infer.c:637-651 : out[d] = W[d][n] . x[n], strictly left-to-right per row */
 void nor_matvec_f32(float *out, const float *x, const uint8_t *w_bytes, int n, int d) {
-    #pragma omp parallel for
+    #pragma omp parallel for NOR_PAR((long)d * n)
     for (int r = 0; r < d; r++) {
         const uint8_t *row = w_bytes + (size_t)r * n * 4;
         float acc = 0.0f;
@@ -98,7 +106,7 @@ void nor_q80_quantize(int8_t *codes, float *scales, const float *x, int n, int g
 void nor_matvec_q80(float *out, const int8_t *xq, const float *xs, const int8_t *wq, const uint8_t *ws_bytes,
                     int n, int d, int gs) {
     int ngroups = n / gs;
-    #pragma omp parallel for
+    #pragma omp parallel for NOR_PAR((long)d * n)
     for (int r = 0; r < d; r++) {
         const int8_t *wrow = wq + (size_t)r * n;
         float acc = 0.0f;
@@ -252,7 +260,7 @@ static float q4k_block_dot(const uint8_t *p, const uint8_t *q) {
  * offset is only right in those cases). blocks_out: nblk*160 bytes, zero-filled. */
 void nor_q4k_quantize_rows(uint8_t *blocks_out, const float *x, uint64_t nrows, uint32_t n) {
     uint32_t bpr = (n + 255) / 256;
-    #pragma omp parallel for
+    #pragma omp parallel for NOR_PAR((long)nrows * n)
     for (uint64_t r = 0; r < nrows; r++) {
         for (uint32_t j = 0; j < bpr; j++) {
             uint32_t len = (n >= (j + 1) * 256) ? 256 : (n - j * 256);
@@ -264,7 +272,7 @@ void nor_q4k_quantize_rows(uint8_t *blocks_out, const float *x, uint64_t nrows, 
 /* tensor.c:438-471 : rows [row0,row0+d) of a block array with bpr blocks per row */
 void nor_matvec_q4k(float *out, const uint8_t *xblocks, const uint8_t *wblocks, uint64_t row0, uint32_t d, uint32_t n) {
     uint32_t bpr = (n + 255) / 256;
-    #pragma omp parallel for
+    #pragma omp parallel for NOR_PAR((long)d * n)
     for (uint32_t r = 0; r < d; r++) {
         const uint8_t *wrow = wblocks + (row0 + r) * bpr * NOR_Q4K_BLOCK_BYTES;
         float acc = 0.0f;
@@ -489,7 +497,7 @@ static void layer_forward(NorModel *m, uint32_t layer, uint32_t pos, int causal)
     probe(m, (int)layer, NOR_PH_MHA, krow, vrow);
 
     uint32_t span = causal ? pos + 1 : S;                /* infer.c:841-879 */
-    #pragma omp parallel for
+    #pragma omp parallel for NOR_PAR((long)m->H * span * hd * 8)
     for (uint32_t h = 0; h < m->H; h++) {
         const float *qh = m->q + h * hd;
         float *att = m->att + (uint64_t)h * S;
