@@ -236,6 +236,8 @@ def main():
     ap.add_argument("--mode", default="replicas", choices=["replicas"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact", action="store_true", help="run the engine in exact (reference-order) mode")
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -255,7 +257,8 @@ def main():
     if dist is not None:
         dist.barrier()
     path = mf.cached_model(spec, quant, gs or 128)           # every rank finds the file rank 0 wrote
-    eng = E.Engine(path, seq, device=local, flags=E.FLAG_EXACT if args.exact else 0)
+    flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0)
+    eng = E.Engine(path, seq, device=local, flags=flags)
     n_dec = seq - PROMPT
 
     # ---- warm-up (also brings clocks up) ----

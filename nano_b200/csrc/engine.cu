@@ -249,7 +249,19 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.xba = e->xba;
         a.ws_m = e->ws_m; a.ws_l = e->ws_l; a.ws_acc = e->ws_acc; a.ticket = e->tickets;
         a.st = e->st; a.nsplit_max = e->nsplit_max; a.chunk_cap = e->chunk_cap; a.d = d;
-        if ((r = launch<AttnArgs>(e, k_attention, dim3(e->nsplit_max, d.KV), dim3(kAttnThreads), e->attn_smem, a))) return r;
+        void (*kern)(const AttnArgs) = k_attention;
+        uint32_t smem = e->attn_smem;
+        if (d.hd <= 128 && !getenv("NB200_GENERIC_ATTN")) {
+            switch (d.kv_mul) {
+                case 1: kern = k_attention_fast<1>; break;
+                case 2: kern = k_attention_fast<2>; break;
+                case 4: kern = k_attention_fast<4>; break;
+                case 8: kern = k_attention_fast<8>; break;
+                default: break;
+            }
+            if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max) * 4u;
+        }
+        if ((r = launch<AttnArgs>(e, kern, dim3(e->nsplit_max, d.KV), dim3(kAttnThreads), smem, a))) return r;
     } else {
         AttnExactArgs a{};
         a.q = e->q; a.kraw = e->kraw; a.kc = e->kc + l * kvl; a.vc = e->vc + l * kvl;

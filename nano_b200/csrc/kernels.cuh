@@ -83,6 +83,7 @@ __device__ __forceinline__ int4 ldg_stream16(const void *p) {
         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -465,17 +466,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
     __shared__ uint32_t is_last;
 
     pdl_launch_dependents();
-    pdl_wait();
 
     const Dims &d = a.d;
     const bool exact = d.exact != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblocks = (a.rows + RB - 1) / RB;
+    const uint32_t gwarp = blockIdx.x * kWarps + warp, nwarps = gridDim.x * kWarps;
+
+    // Weights never depend on activations: pull this warp's first row blocks towards L2 before waiting
+    // for the producer kernel, so the HBM latency hides behind the wait and the activation prologue.
+    {
+        const uint32_t rowbytes = (QUANT == 0x00) ? a.n * 4u : (QUANT == 0x80) ? a.n : a.n / 2u;
+        const uint32_t blkbytes = RB * rowbytes;
+        uint32_t it = 0;
+        for (uint32_t rb = gwarp; rb < nblocks && it < 4; rb += nwarps, it++) {
+            const char *base = static_cast<const char *>(a.w) + (size_t)rb * blkbytes;
+            for (uint32_t off = lane * 128u; off < blkbytes; off += 32u * 128u) prefetch_l2(base + off);
+        }
+    }
+    pdl_wait();
+
     if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), red);
     else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, d.gs, exact, act, red, a.dump_codes, a.dump_scales);
     else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, red, a.dump_codes, a.dump_scales);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nblocks = (a.rows + RB - 1) / RB;
-    const uint32_t gwarp = blockIdx.x * kWarps + warp, nwarps = gridDim.x * kWarps;
     const uint32_t pos = a.st ? a.st->pos : 0;
 
     float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
@@ -519,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
                     }
                 } else if (EPI == EPI_CLS) {
                     // infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037
-                    if (a.seen[row]) v = __fdiv_rn(v, pen);
+                    if (pen != 1.0f && a.seen[row]) v = __fdiv_rn(v, pen);      // x / 1.0f == x: skip the lookup
                     if (lane == 0) a.out[row] = v;
                     if (v > bestv) { bestv = v; besti = row; }
                 }
@@ -541,14 +555,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
             is_last = (t == gridDim.x - 1) ? 1u : 0u;
         }
         __syncthreads();
-        if (is_last && threadIdx.x == 0) {
+        if (is_last) {
             __threadfence();
+            // all threads fetch partials in parallel (a serial loop of L2 round trips costs ~40 us)
             float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
-            for (uint32_t c = 0; c < gridDim.x; c++) {
+            for (uint32_t c = threadIdx.x; c < gridDim.x; c += kThreads) {
                 const float v = __ldcg(a.cls_val + c); const uint32_t i = __ldcg(a.cls_idx + c);
-                if (i == 0xffffffffu) continue;
-                if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+                if (i != 0xffffffffu && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi != 0xffffffffu && (ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+            }
+            __syncthreads();
+            if (lane == 0) { best_v[warp] = bv; best_i[warp] = bi; }
+            __syncthreads();
+        }
+        if (is_last && threadIdx.x == 0) {
+            float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
+            for (int w = 0; w < kWarps; w++)
+                if (best_i[w] != 0xffffffffu && (best_v[w] > bv || (best_v[w] == bv && best_i[w] < bi))) { bv = best_v[w]; bi = best_i[w]; }
             if (bi == 0xffffffffu) bi = 0;     // all-NaN row: the reference's argmax returns index 0
             DevState *st = a.st_rw;
             st->cls_ticket = 0;
@@ -697,6 +724,166 @@ __device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict
         }
     }
     __syncwarp();
+}
+
+// Fast path (hd <= 128, kv_mul in {1,2,4,8}): one CTA = (kv head g, split).  K and V rows are read once for
+// all KVM query heads of the group; softmax statistics are per-warp (no block barriers); the last CTA of
+// the kv head merges the splits with all threads.
+// smem (floats): qs[KVM*hd] | krow[hd] | sc[KVM*chunk_cap] | wsc[KVM*nsplit_max] | stat[2*KVM] | part[8*rpw*KVM*hd]
+__host__ __device__ inline uint32_t attn_fast_smem_floats(uint32_t kvm, uint32_t hd, uint32_t chunk_cap, uint32_t nsplit_max) {
+    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
+    const uint32_t rpw = 32 / lpr;
+    return kvm * hd + hd + kvm * chunk_cap + kvm * nsplit_max + 2 * kvm + 8 + kAttnWarps * rpw * kvm * hd;
+}
+
+template <int KVM>
+__global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ uint32_t is_last;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const Dims &d = a.d;
+    const uint32_t hd = d.hd;
+    const uint32_t g = blockIdx.y, split = blockIdx.x;
+    const uint32_t pos = a.st->pos;
+    const uint32_t range = a.st->is_causal ? pos + 1 : d.max_seq;
+    uint32_t chunk = (range + a.nsplit_max - 1) / a.nsplit_max;
+    chunk = max(chunk, 32u);
+    chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
+    const uint32_t nsplit = (range + chunk - 1) / chunk;
+    if (split >= nsplit) return;
+    const uint32_t t0 = split * chunk, t1 = min(range, t0 + chunk), len = t1 - t0;
+    const bool owner = (pos >= t0 && pos < t1);
+    const uint32_t cap = a.chunk_cap;
+
+    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
+    const uint32_t rpw = 32 / lpr;
+    float *qs = sm;
+    float *krow = qs + KVM * hd;
+    float *sc = krow + hd;
+    float *wsc = sc + KVM * cap;
+    float *stat = wsc + KVM * a.nsplit_max;
+    float *part = sm + (((uint32_t)(stat - sm) + 2 * KVM + 3) & ~3u);       // 16-byte aligned
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sub = lane / lpr, li = lane % lpr;
+    const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
+
+    for (uint32_t i = threadIdx.x; i < KVM * hd; i += kAttnThreads) qs[i] = a.q[(size_t)g * KVM * hd + i];
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) krow[i] = a.kraw[(size_t)g * hd + i];
+    __syncthreads();
+    for (uint32_t m = warp; m < KVM + (owner ? 1u : 0u); m += kAttnWarps) {
+        if (m < KVM) head_norm_rope(qs + m * hd, a.qnorm, cr, ci, d, false);
+        else head_norm_rope(krow, a.knorm, cr, ci, d, false);
+    }
+    __syncthreads();
+    float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) kbase[(size_t)pos * hd + i] = krow[i];
+    const float dv = sqrtf((float)hd);
+    const uint32_t col = li * 4;
+    const bool colon = col < hd;
+
+    // ---- scores for all KVM heads from one pass over K ----
+    float4 qv[KVM];
+#pragma unroll
+    for (int m = 0; m < KVM; m++) qv[m] = colon ? *reinterpret_cast<const float4 *>(qs + m * hd + col) : make_float4(0, 0, 0, 0);
+    for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+        const uint32_t tl = tb + sub;
+        float4 kv = make_float4(0, 0, 0, 0);
+        if (tl < len && colon) {
+            const uint32_t t = t0 + tl;
+            const float *kr = (t == pos) ? krow : kbase + (size_t)t * hd;
+            kv = *reinterpret_cast<const float4 *>(kr + col);
+        }
+#pragma unroll
+        for (int m = 0; m < KVM; m++) {
+            float acc = kv.x * qv[m].x;
+            acc = fmaf(kv.y, qv[m].y, acc); acc = fmaf(kv.z, qv[m].z, acc); acc = fmaf(kv.w, qv[m].w, acc);
+            for (uint32_t o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (tl < len && li == 0) sc[m * cap + tl] = __fdiv_rn(acc, dv);
+        }
+    }
+    __syncthreads();
+    // ---- per-head softmax statistics, one warp per head ----
+    if (warp < KVM) {
+        float *s = sc + warp * cap;
+        float mx = -FLT_MAX;
+        for (uint32_t t = lane; t < len; t += 32) mx = fmaxf(mx, s[t]);
+        mx = warp_max(mx);
+        float ls = 0.0f;
+        for (uint32_t t = lane; t < len; t += 32) { const float e = expf(s[t] - mx); s[t] = e; ls += e; }
+        ls = warp_sum(ls);
+        if (lane == 0) { stat[2 * warp] = mx; stat[2 * warp + 1] = ls; }
+    }
+    __syncthreads();
+    // ---- weighted V for all KVM heads from one pass over V ----
+    float4 av[KVM];
+#pragma unroll
+    for (int m = 0; m < KVM; m++) av[m] = make_float4(0, 0, 0, 0);
+    for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+        const uint32_t tl = tb + sub;
+        if (tl < len && colon) {
+            const float4 vv = *reinterpret_cast<const float4 *>(vbase + (size_t)(t0 + tl) * hd + col);
+#pragma unroll
+            for (int m = 0; m < KVM; m++) {
+                const float e = sc[m * cap + tl];
+                av[m].x = fmaf(e, vv.x, av[m].x); av[m].y = fmaf(e, vv.y, av[m].y);
+                av[m].z = fmaf(e, vv.z, av[m].z); av[m].w = fmaf(e, vv.w, av[m].w);
+            }
+        }
+    }
+    if (colon) {
+#pragma unroll
+        for (int m = 0; m < KVM; m++)
+            *reinterpret_cast<float4 *>(part + ((size_t)(warp * rpw + sub) * KVM + m) * hd + col) = av[m];
+    }
+    __syncthreads();
+    const uint32_t np = kAttnWarps * rpw;
+    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += kAttnThreads) {
+        const uint32_t m = idx / hd, i = idx % hd;
+        float s = 0.0f;
+        for (uint32_t p = 0; p < np; p++) s += part[((size_t)p * KVM + m) * hd + i];
+        a.ws_acc[((size_t)(g * KVM + m) * a.nsplit_max + split) * hd + i] = s;
+    }
+    if (threadIdx.x < KVM) {
+        const size_t slot = (size_t)(g * KVM + threadIdx.x) * a.nsplit_max + split;
+        a.ws_m[slot] = stat[2 * threadIdx.x]; a.ws_l[slot] = stat[2 * threadIdx.x + 1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(a.ticket + g, 1u);
+        is_last = (t == nsplit - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- merge: warp m computes exp(m_s - M) / L for its head; then all threads combine ----
+    if (warp < KVM) {
+        const size_t base = (size_t)(g * KVM + warp) * a.nsplit_max;
+        float M = -FLT_MAX;
+        for (uint32_t s = lane; s < nsplit; s += 32) M = fmaxf(M, __ldcg(a.ws_m + base + s));
+        M = warp_max(M);
+        float L = 0.0f;
+        for (uint32_t s = lane; s < nsplit; s += 32) {
+            const float w = expf(__ldcg(a.ws_m + base + s) - M);
+            wsc[warp * a.nsplit_max + s] = w;
+            L += __ldcg(a.ws_l + base + s) * w;
+        }
+        L = warp_sum(L);
+        if (lane == 0) stat[2 * warp] = L;
+    }
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += kAttnThreads) {
+        const uint32_t m = idx / hd, i = idx % hd;
+        const size_t base = (size_t)(g * KVM + m) * a.nsplit_max;
+        float o = 0.0f;
+#pragma unroll 4
+        for (uint32_t s = 0; s < nsplit; s++) o = fmaf(__ldcg(a.ws_acc + (base + s) * hd + i), wsc[m * a.nsplit_max + s], o);
+        a.xba[(size_t)(g * KVM + m) * hd + i] = __fdiv_rn(o, stat[2 * m]);
+    }
+    if (threadIdx.x == 0) a.ticket[g] = 0;
 }
 
 __global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {

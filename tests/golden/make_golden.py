@@ -66,6 +66,27 @@ def main():
         print(key, out[key].shape, float(np.abs(out[key]).max()))
     np.savez_compressed(os.path.join(HERE, "toy_logits.npz"), **out)
 
+    # Noise floor of the reference itself: max |logit(fast build) - logit(strict build)| of the SAME source on the
+    # SAME file (SURVEY finding 11).  The fast-mode GPU tolerance is max(north-star tolerance, 1.5 x this floor).
+    floors = {}
+    S = 40
+    for name, quant, gs in TOY_CONFIGS + [("mini-qwen3", mf.QUANT_Q80, 128), ("mini-nano", mf.QUANT_Q80, 128), ("mini-nano", mf.QUANT_Q4K, 128)]:
+        spec = mf.PRESETS[name]
+        path = mf.cached_model(spec, quant, gs)
+        a = ob.RefEngine(path, S, "strict")
+        toks = mf.teacher_tokens(S, spec.vocab)
+        strict = [a.forward(toks[p], p) for p in range(S)]
+        worst = 0.0
+        for fl in ("fast_v3", "fast_v4"):
+            b = ob.RefEngine(path, S, fl)
+            for p in range(S):
+                worst = max(worst, float(np.abs(b.forward(toks[p], p) - strict[p]).max()))
+            b.close()
+        a.close()
+        floors[f"{name}_{quant:02x}_{gs}"] = worst
+    json.dump(floors, open(os.path.join(HERE, "reference_noise_floor.json"), "w"), indent=1)
+    print("floors", floors)
+
     # Q4K KAT
     L = ob.RefEngine.lib("strict")
     d, n = 8, 768
