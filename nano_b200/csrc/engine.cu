@@ -98,6 +98,8 @@ struct nb200_engine {
     uint32_t nsplit_max = 1, chunk_cap = 32, attn_smem = 0, cls_grid = 1;
     cudaGraphExec_t graph = nullptr;
     bool use_pdl = true;
+    // persistent megakernel (fast mode): one cooperative launch runs n tokens
+    bool use_mega = false; const void *mega_kern = nullptr; uint32_t mega_smem = 0; LayerW *layers_dev = nullptr; unsigned int *bar = nullptr;
     uint64_t launches = 0, weight_bytes = 0;
     uint32_t launches_per_token = 0;
     std::vector<uint32_t> seen_mirror;   // ids whose seen[] flag is set, by position
@@ -179,7 +181,8 @@ int grid_mult() {
 int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, int num_sms) {
     const Dims &d = a.d;
     a.w = m.w; a.w_aux = m.aux; a.rows = m.rows; a.n = m.n;
-    const uint32_t smem = act_smem_bytes(d.quant, m.n, d.gs ? d.gs : 1, d.exact && norm);
+    const uint32_t smem = act_smem_bytes(d.quant, m.n, d.gs ? d.gs : 1);
+    (void)norm;
     if (d.quant == 0x00u && d.exact) {
         MatvecKern k = nullptr;
         switch (epi) {
@@ -259,7 +262,7 @@ int run_layer(nb200_engine *e, uint32_t l) {
                 case 8: kern = k_attention_fast<8>; break;
                 default: break;
             }
-            if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max) * 4u;
+            if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kAttnWarps) * 4u;
         }
         if ((r = launch<AttnArgs>(e, kern, dim3(e->nsplit_max, d.KV), dim3(kAttnThreads), smem, a))) return r;
     } else {
@@ -312,7 +315,48 @@ int run_token(nb200_engine *e) {
     return run_classifier(e);
 }
 
+typedef void (*MegaKern)(const MegaArgs);
+
+template <int QUANT, int LPG>
+MegaKern pick_mega_kvm(uint32_t kvm) {
+    switch (kvm) {
+        case 1: return k_decode_mega<QUANT, LPG, 1>;
+        case 2: return k_decode_mega<QUANT, LPG, 2>;
+        case 4: return k_decode_mega<QUANT, LPG, 4>;
+        default: return nullptr;
+    }
+}
+
+MegaKern pick_mega(const Dims &d) {
+    if (d.hd > 128) return nullptr;
+    if (d.quant == 0x00u) return pick_mega_kvm<0x00, 8>(d.kv_mul);
+    if (d.quant == 0x42u) return pick_mega_kvm<0x42, 8>(d.kv_mul);
+    if (d.gs == 128) return pick_mega_kvm<0x80, 8>(d.kv_mul);
+    if (d.gs == 64) return pick_mega_kvm<0x80, 4>(d.kv_mul);
+    return nullptr;
+}
+
+// n_steps tokens in ONE cooperative launch of the persistent kernel
+int launch_mega(nb200_engine *e, uint32_t n_steps) {
+    if (n_steps == 0) return 0;
+    MegaArgs g{};
+    g.layers = e->layers_dev;
+    g.cls_w = e->cls.w; g.cls_aux = e->cls.aux; g.emb_w = e->emb.w; g.emb_aux = e->emb.aux;
+    g.g_final = e->norm_final; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
+    g.x = e->x; g.q = e->q; g.kraw = e->kraw; g.xba = e->xba; g.hb = e->hb; g.logits = e->logits;
+    g.ws_m = e->ws_m; g.ws_l = e->ws_l; g.ws_acc = e->ws_acc; g.ticket = e->tickets;
+    g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.cls_val = e->cls_val; g.cls_idx = e->cls_idx;
+    g.bar = e->bar; g.n_steps = n_steps; g.nsplit_max = e->nsplit_max; g.chunk_cap = e->chunk_cap;
+    g.dump_codes = e->dump_codes; g.dump_scales = e->dump_scales; g.d = e->d;
+    CK(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), e->stream));
+    void *params[] = {&g};
+    CK(cudaLaunchCooperativeKernel(e->mega_kern, dim3(e->cls_grid), dim3(kThreads), params, e->mega_smem, e->stream));
+    e->launches++;
+    return 0;
+}
+
 int launch_token(nb200_engine *e) {
+    if (e->use_mega) return launch_mega(e, 1);
     if (e->graph) {
         CK(cudaGraphLaunch(e->graph, e->stream));
         e->launches += e->launches_per_token;
@@ -580,7 +624,12 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     DM(e->kc, kv_floats * 4); DM(e->vc, kv_floats * 4);
     CK(cudaMemset(e->kc, 0, kv_floats * 4)); CK(cudaMemset(e->vc, 0, kv_floats * 4));   // calloc'd in the reference (infer.c:47)
     CK(cudaMemset(e->x, 0, E * 4)); CK(cudaMemset(e->logits, 0, V * 4));
-    uint32_t nsm = (uint32_t)(2 * e->num_sms + d.KV - 1) / d.KV;
+    const char *mega_env = getenv("NB200_MEGA");
+    MegaKern mk = (d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0)) ? nullptr : pick_mega(d);
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) mk = nullptr;
+    uint32_t nsm = mk ? (uint32_t)e->num_sms / d.KV : (uint32_t)(2 * e->num_sms + d.KV - 1) / d.KV;
     if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
     e->nsplit_max = nsm;
     uint32_t cap = (d.max_seq + nsm - 1) / nsm; cap = (cap + 7u) & ~7u; if (cap < 32) cap = 32;
@@ -603,7 +652,36 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     memset(e->st_host, 0, sizeof(DevState));
     CK(cudaDeviceSynchronize());
 
-    if (!(flags & NB200_FLAG_NO_GRAPH)) {
+    if (mk) {
+        // persistent kernel: dynamic smem = largest phase (activation prep of n in {E, q_dim, F}; attention item)
+        uint32_t sm = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kWarps) * 4u;
+        const uint32_t ns[3] = {d.E, d.q_dim, d.F};
+        for (uint32_t n : ns) { const uint32_t b = act_smem_bytes(d.quant, n, d.gs ? d.gs : 1); if (b > sm) sm = b; }
+        int occ = 0;
+        cudaError_t ce = cudaFuncSetAttribute((const void *)mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)mk, kThreads, sm);
+        if (ce == cudaSuccess && occ >= 1) {
+            std::vector<LayerW> lw(L);
+            const size_t kvl = (size_t)d.KV * d.max_seq * d.hd;
+            for (uint64_t l = 0; l < L; l++) {
+                lw[l].qkv_w = e->qkv[l].w; lw[l].qkv_aux = e->qkv[l].aux; lw[l].wo_w = e->wo[l].w; lw[l].wo_aux = e->wo[l].aux;
+                lw[l].w13_w = e->w13[l].w; lw[l].w13_aux = e->w13[l].aux; lw[l].w2_w = e->w2[l].w; lw[l].w2_aux = e->w2[l].aux;
+                lw[l].g_attn = e->norm_attn + l * E; lw[l].g_ffn = e->norm_ffn + l * E;
+                lw[l].qnorm = e->qnorm ? e->qnorm + l * d.hd : nullptr; lw[l].knorm = e->knorm ? e->knorm + l * d.hd : nullptr;
+                lw[l].kc = e->kc + l * kvl; lw[l].vc = e->vc + l * kvl;
+            }
+            DM(e->layers_dev, L * sizeof(LayerW));
+            CK(cudaMemcpy(e->layers_dev, lw.data(), L * sizeof(LayerW), cudaMemcpyHostToDevice));
+            DM(e->bar, 64); CK(cudaMemset(e->bar, 0, 64));
+            e->mega_kern = (const void *)mk; e->mega_smem = sm; e->use_mega = true;
+            e->launches_per_token = 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (e->use_mega) {
+        // nothing to capture: a token (or a whole run of tokens) is one cooperative launch
+    } else if (!(flags & NB200_FLAG_NO_GRAPH)) {
         r = capture_graph(e);
         if (r && e->use_pdl) {          // retry without PDL edges before giving up on the graph
             e->use_pdl = false;
@@ -705,9 +783,11 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
     e->seen_valid = false; e->seen_mirror.clear();
     CK(cudaEventRecord(ev[0], e->stream));
-    for (uint32_t p = 0; p + 1 < n_prompt; p++) if ((r = launch_token(e))) return r;
+    if (e->use_mega) { if ((r = launch_mega(e, n_prompt - 1))) return r; }
+    else for (uint32_t p = 0; p + 1 < n_prompt; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[1], e->stream));
-    for (uint32_t p = n_prompt - 1; p + 1 < n_total; p++) if ((r = launch_token(e))) return r;
+    if (e->use_mega) { if ((r = launch_mega(e, n_total - n_prompt))) return r; }
+    else for (uint32_t p = n_prompt - 1; p + 1 < n_total; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[2], e->stream));
     CK(cudaMemcpyAsync(ids, e->ids_dev, (size_t)n_total * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -823,7 +903,7 @@ int op_prep(uint32_t quant, const float *x, const float *gain, uint32_t n, uint3
         (r = dcodes.alloc((size_t)n * 2 + 64)) || (r = dscales.alloc((size_t)n * 4 + 64))) return r;
     CK(cudaMemcpy(dx.p, x, (size_t)n * 4, cudaMemcpyHostToDevice));
     if (gain) CK(cudaMemcpy(dg.p, gain, (size_t)n * 4, cudaMemcpyHostToDevice));
-    const uint32_t smem = act_smem_bytes(quant, n, gs ? gs : 1, exact && gain);
+    const uint32_t smem = act_smem_bytes(quant, n, gs ? gs : 1);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute((const void *)k_op_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_op_prep<<<1, kThreads, smem>>>(dx.as<float>(), gain ? dg.as<float>() : nullptr, n, gs, quant, exact, dout.as<float>(),
                                      dcodes.as<int8_t>(), dscales.as<float>());

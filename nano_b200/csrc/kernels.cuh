@@ -125,20 +125,27 @@ __device__ __forceinline__ int nearest_int_magic(float f) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// infer.c:601-614.  fast: tree sum; exact: the reference's sequential sum (thread 0 over a smem copy).
+// Stage the fp32 source vector into shared memory with L2 (.cg) loads: the vector was produced by other
+// CTAs (another kernel, or another phase of the persistent kernel), so it must not come from L1 / the
+// non-coherent path.
 template <int NT>
-__device__ __forceinline__ float rms_inverse(const float *__restrict__ x, int n, bool exact, float *red, float *scratch) {
+__device__ __forceinline__ void stage_vector(const float *src, int n, float *stage) {
+    for (int i = threadIdx.x; i < n; i += NT) stage[i] = __ldcg(src + i);
+    __syncthreads();
+}
+
+// infer.c:601-614 over the staged vector.  fast: tree sum; exact: the reference's sequential sum (thread 0).
+template <int NT>
+__device__ __forceinline__ float rms_inverse(const float *stage, int n, bool exact, float *red) {
     float ss;
     if (!exact) {
         float acc = 0.0f;
-        for (int i = threadIdx.x; i < n; i += NT) { float v = x[i]; acc = fmaf(v, v, acc); }
+        for (int i = threadIdx.x; i < n; i += NT) { const float v = stage[i]; acc = fmaf(v, v, acc); }
         ss = block_sum<NT>(acc, red);
     } else {
-        for (int i = threadIdx.x; i < n; i += NT) scratch[i] = x[i];
-        __syncthreads();
         if (threadIdx.x == 0) {
             float acc = 0.0f;
-            for (int i = 0; i < n; i++) acc = __fadd_rn(acc, __fmul_rn(scratch[i], scratch[i]));
+            for (int i = 0; i < n; i++) acc = __fadd_rn(acc, __fmul_rn(stage[i], stage[i]));
             red[0] = acc;
         }
         __syncthreads();
@@ -150,45 +157,47 @@ __device__ __forceinline__ float rms_inverse(const float *__restrict__ x, int n,
     return __fdiv_rn(1.0f, __fsqrt_rn(ss));
 }
 
-__device__ __forceinline__ float act_value(const float *__restrict__ src, const float *__restrict__ gain, float inv, int i) {
-    float v = src[i];
-    return gain ? __fmul_rn(gain[i], __fmul_rn(inv, v)) : v;
+__device__ __forceinline__ float act_value(const float *stage, const float *__restrict__ gain, float inv, int i) {
+    const float v = stage[i];
+    return gain ? __fmul_rn(__ldg(gain + i), __fmul_rn(inv, v)) : v;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Activation preparation into shared memory (each CTA redoes it: <= 39 KB of L2 reads, no grid sync)
-// smem layouts:
+// smem layouts (followed by the fp32 staging copy of the source, n floats):
 //   F32 : float v[n]
 //   Q80 : int8 codes[n] | pad16 | float scales[n/gs]
 //   Q4K : u32 xe[n/8] (even elements) | u32 xo[n/8] (odd elements) | float4 {sq,bq,sum_q,0}[n/32]
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, uint32_t gs, bool exact_norm) {
+__host__ __device__ inline uint32_t act_region_bytes(uint32_t quant, uint32_t n, uint32_t gs) {
     uint32_t b;
     if (quant == 0x00u) b = n * 4u;
     else if (quant == 0x80u) b = ((n + 15u) & ~15u) + (n / gs) * 4u + 16u;
     else b = n + (n / 32u) * 16u;
-    if (exact_norm && b < n * 4u) b = n * 4u;     // exact rmsnorm stages x as fp32 before quantising
     return (b + 15u) & ~15u;
+}
+__host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, uint32_t gs) {
+    return act_region_bytes(quant, n, gs) + n * 4u;      // + staging copy
 }
 
 template <int NT>
-__device__ void prep_f32(const float *__restrict__ src, const float *__restrict__ gain, int n, bool exact,
-                         float *act, float *red) {
+__device__ void prep_f32(const float *src, const float *__restrict__ gain, int n, bool exact, float *act, float *stage, float *red) {
+    stage_vector<NT>(src, n, stage);
     float inv = 1.0f;
-    if (gain) inv = rms_inverse<NT>(src, n, exact, red, act);
-    for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(src, gain, inv, i);
+    if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
+    for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(stage, gain, inv, i);
     __syncthreads();
 }
 
 // tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
 template <int NT>
-__device__ void prep_q80(const float *__restrict__ src, const float *__restrict__ gain, int n, int gs, bool exact,
-                         unsigned char *act, float *red, int8_t *dump_codes, float *dump_scales) {
+__device__ void prep_q80(const float *src, const float *__restrict__ gain, int n, int gs, bool exact,
+                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales) {
     int8_t *codes = reinterpret_cast<int8_t *>(act);
     float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
+    stage_vector<NT>(src, n, stage);
     float inv = 1.0f;
-    if (gain) inv = rms_inverse<NT>(src, n, exact, red, reinterpret_cast<float *>(act));
-    __syncthreads();
+    if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = n / gs, epl = gs / 32;      // elements per lane (gs in {32,64,128,256})
     for (int g = warp; g < G; g += NT / 32) {
@@ -197,7 +206,7 @@ __device__ void prep_q80(const float *__restrict__ src, const float *__restrict_
         const int base = g * gs + lane * epl;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (j < epl) { v[j] = act_value(src, gain, inv, base + j); amax = fmaxf(amax, fabsf(v[j])); }
+            if (j < epl) { v[j] = act_value(stage, gain, inv, base + j); amax = fmaxf(amax, fabsf(v[j])); }
         }
         amax = warp_max(amax);
         const float sc = __fdiv_rn(amax, 127.0f);
@@ -223,14 +232,14 @@ __device__ void prep_q80(const float *__restrict__ src, const float *__restrict_
 //   dump_scales[n/256..2n/256) = sbias
 //   dump_codes[n .. n + n/32)  = s6, dump_codes[n + n/32 .. n + 2n/32) = b6
 template <int NT>
-__device__ void prep_q4k(const float *__restrict__ src, const float *__restrict__ gain, int n, bool exact,
-                         unsigned char *act, float *red, int8_t *dump_codes, float *dump_scales) {
+__device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n, bool exact,
+                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales) {
     uint32_t *xe = reinterpret_cast<uint32_t *>(act);
     uint32_t *xo = reinterpret_cast<uint32_t *>(act + n / 2);
     float4 *gp = reinterpret_cast<float4 *>(act + n);
+    stage_vector<NT>(src, n, stage);
     float inv = 1.0f;
-    if (gain) inv = rms_inverse<NT>(src, n, exact, red, reinterpret_cast<float *>(act));
-    __syncthreads();
+    if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NB = n / 256;
     const bool dump = dump_codes && blockIdx.x == 0;
@@ -240,7 +249,7 @@ __device__ void prep_q4k(const float *__restrict__ src, const float *__restrict_
         const int base = b * 256 + lane * 8;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            v[j] = act_value(src, gain, inv, base + j);
+            v[j] = act_value(stage, gain, inv, base + j);
             if (v[j] > hi) hi = v[j];
             if (v[j] < lo) lo = v[j];
         }
@@ -455,46 +464,49 @@ __device__ __forceinline__ void rows_q4k(const uint8_t *__restrict__ W, const ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// The fused matvec kernel: [PDL prologue] -> activation prep -> row blocks -> epilogue
+// One fused matvec phase = activation prep -> row blocks -> epilogue, executed by `ncta` cooperating CTAs
+// (a whole kernel grid in the multi-kernel path, or the persistent grid of k_decode_mega).
 // ------------------------------------------------------------------------------------------------
+struct MatvecSmem {
+    float red[32];
+    float best_v[kWarps];
+    uint32_t best_i[kWarps];
+    uint32_t flag;
+};
+
+// Weights never depend on activations: pull a warp's first row blocks of a matrix towards L2 ahead of time
+// (before the PDL wait / before a grid barrier), so the HBM latency hides behind the wait.
+template <int QUANT, int RB>
+__device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows, uint32_t n, uint32_t cta, uint32_t ncta, uint32_t max_iters) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblocks = (rows + RB - 1) / RB;
+    const uint32_t gwarp = cta * kWarps + warp, nwarps = ncta * kWarps;
+    const uint32_t rowbytes = (QUANT == 0x00) ? n * 4u : (QUANT == 0x80) ? n : n / 2u;
+    const uint32_t blkbytes = RB * rowbytes;
+    uint32_t it = 0;
+    for (uint32_t rb = gwarp; rb < nblocks && it < max_iters; rb += nwarps, it++) {
+        const char *base = static_cast<const char *>(w) + (size_t)rb * blkbytes;
+        for (uint32_t off = lane * 128u; off < blkbytes; off += 32u * 128u) prefetch_l2(base + off);
+    }
+}
+
 template <int QUANT, int EPI, int RB, int LPG>
-__global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
-    extern __shared__ __align__(16) unsigned char act[];
-    __shared__ float red[32];
-    __shared__ float best_v[kWarps];
-    __shared__ uint32_t best_i[kWarps];
-    __shared__ uint32_t is_last;
-
-    pdl_launch_dependents();
-
+__device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, uint32_t ncta, unsigned char *act, MatvecSmem &ms) {
     const Dims &d = a.d;
     const bool exact = d.exact != 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblocks = (a.rows + RB - 1) / RB;
-    const uint32_t gwarp = blockIdx.x * kWarps + warp, nwarps = gridDim.x * kWarps;
+    const uint32_t gwarp = cta * kWarps + warp, nwarps = ncta * kWarps;
+    float *stage = reinterpret_cast<float *>(act + act_region_bytes(QUANT, a.n, (QUANT == 0x80) ? LPG * 16 : 1));
 
-    // Weights never depend on activations: pull this warp's first row blocks towards L2 before waiting
-    // for the producer kernel, so the HBM latency hides behind the wait and the activation prologue.
-    {
-        const uint32_t rowbytes = (QUANT == 0x00) ? a.n * 4u : (QUANT == 0x80) ? a.n : a.n / 2u;
-        const uint32_t blkbytes = RB * rowbytes;
-        uint32_t it = 0;
-        for (uint32_t rb = gwarp; rb < nblocks && it < 4; rb += nwarps, it++) {
-            const char *base = static_cast<const char *>(a.w) + (size_t)rb * blkbytes;
-            for (uint32_t off = lane * 128u; off < blkbytes; off += 32u * 128u) prefetch_l2(base + off);
-        }
-    }
-    pdl_wait();
+    if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red);
+    else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
+    else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
 
-    if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), red);
-    else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, d.gs, exact, act, red, a.dump_codes, a.dump_scales);
-    else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, red, a.dump_codes, a.dump_scales);
-
-    const uint32_t pos = a.st ? a.st->pos : 0;
-
+    const uint32_t pos = a.st ? __ldcg(&a.st->pos) : 0;
     float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
     float pen = 1.0f;
-    if (EPI == EPI_CLS) pen = a.st->penalty;
+    if (EPI == EPI_CLS) pen = __ldcg(&a.st->penalty);
 
     for (uint32_t rb = gwarp; rb < nblocks; rb += nwarps) {
         const uint32_t row0 = rb * RB;
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
                 if (row >= a.rows) break;
                 float v = val[r];
                 if (EPI == EPI_STORE) { if (lane == 0) a.out[row] = v; }
-                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(a.out[row], v); }
+                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(__ldcg(a.out + row), v); }
                 else if (EPI == EPI_QKV) {
                     if (lane == 0) {
                         if (row < d.q_dim) a.out[row] = v;
@@ -542,55 +554,77 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
     }
 
     if (EPI == EPI_CLS) {
-        // rows were visited in ascending order per warp, so (bestv,besti) already holds the first max
-        if (lane == 0) { best_v[warp] = bestv; best_i[warp] = besti; }
+        // rows were visited in ascending order per warp, so (bestv,besti) already holds the warp's first max
+        if (lane == 0) { ms.best_v[warp] = bestv; ms.best_i[warp] = besti; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            float bv = best_v[0]; uint32_t bi = best_i[0];
+            float bv = ms.best_v[0]; uint32_t bi = ms.best_i[0];
             for (int w = 1; w < kWarps; w++)
-                if (best_v[w] > bv || (best_v[w] == bv && best_i[w] < bi)) { bv = best_v[w]; bi = best_i[w]; }
-            a.cls_val[blockIdx.x] = bv; a.cls_idx[blockIdx.x] = bi;
-            __threadfence();
-            const uint32_t t = atomicAdd(&a.st_rw->cls_ticket, 1u);
-            is_last = (t == gridDim.x - 1) ? 1u : 0u;
+                if (ms.best_v[w] > bv || (ms.best_v[w] == bv && ms.best_i[w] < bi)) { bv = ms.best_v[w]; bi = ms.best_i[w]; }
+            a.cls_val[cta] = bv; a.cls_idx[cta] = bi;
         }
         __syncthreads();
-        if (is_last) {
-            __threadfence();
-            // all threads fetch partials in parallel (a serial loop of L2 round trips costs ~40 us)
-            float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
-            for (uint32_t c = threadIdx.x; c < gridDim.x; c += kThreads) {
-                const float v = __ldcg(a.cls_val + c); const uint32_t i = __ldcg(a.cls_idx + c);
-                if (i != 0xffffffffu && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
-            }
+    }
+}
+
+// Final argmax over the per-CTA partials + state update, by ONE full CTA.  Returns (in every thread) the token
+// that the next step will consume (device loop) or the sampled token (API mode).
+__device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t ncta, MatvecSmem &ms) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
+    for (uint32_t c = threadIdx.x; c < ncta; c += kThreads) {      // parallel fetch: a serial loop of L2 round trips costs ~40 us
+        const float v = __ldcg(a.cls_val + c); const uint32_t i = __ldcg(a.cls_idx + c);
+        if (i != 0xffffffffu && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi != 0xffffffffu && (ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-            }
-            __syncthreads();
-            if (lane == 0) { best_v[warp] = bv; best_i[warp] = bi; }
-            __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0xffffffffu && (ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { ms.best_v[warp] = bv; ms.best_i[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bv = -FLT_MAX; bi = 0xffffffffu;
+        for (int w = 0; w < kWarps; w++)
+            if (ms.best_i[w] != 0xffffffffu && (ms.best_v[w] > bv || (ms.best_v[w] == bv && ms.best_i[w] < bi))) { bv = ms.best_v[w]; bi = ms.best_i[w]; }
+        if (bi == 0xffffffffu) bi = 0;     // all-NaN row: the reference's argmax returns index 0
+        DevState *st = a.st_rw;
+        st->cls_ticket = 0;
+        const uint32_t p = __ldcg(&st->pos);
+        uint32_t nxt = bi;
+        if (__ldcg(&st->advance)) {
+            const uint32_t tok_in = __ldcg(a.ids + p);
+            a.seen_rw[tok_in] = 1;                                  // ids[0..p] are "seen" for step p+1
+            const bool forced = (p + 1 < __ldcg(&st->n_prompt));   // infer.c:1250 is_prefilling
+            if (!forced) a.ids[p + 1] = bi; else nxt = __ldcg(a.ids + p + 1);
+            st->pos = p + 1;
         }
-        if (is_last && threadIdx.x == 0) {
-            float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
-            for (int w = 0; w < kWarps; w++)
-                if (best_i[w] != 0xffffffffu && (best_v[w] > bv || (best_v[w] == bv && best_i[w] < bi))) { bv = best_v[w]; bi = best_i[w]; }
-            if (bi == 0xffffffffu) bi = 0;     // all-NaN row: the reference's argmax returns index 0
-            DevState *st = a.st_rw;
-            st->cls_ticket = 0;
-            const uint32_t p = st->pos;
-            if (st->advance) {
-                const uint32_t tok_in = a.ids[p];
-                a.seen_rw[tok_in] = 1;                          // ids[0..p] are "seen" for step p+1
-                const bool forced = (p + 1 < st->n_prompt);    // infer.c:1250 is_prefilling
-                if (!forced) a.ids[p + 1] = bi;
-                st->next_token = forced ? a.ids[p + 1] : bi;
-                st->pos = p + 1;
-            } else {
-                st->next_token = bi;
-            }
+        st->next_token = nxt;
+        ms.flag = nxt;
+    }
+    __syncthreads();
+    return ms.flag;
+}
+
+template <int QUANT, int EPI, int RB, int LPG>
+__global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
+    extern __shared__ __align__(16) unsigned char act[];
+    __shared__ MatvecSmem ms;
+    pdl_launch_dependents();
+    prefetch_row_blocks<QUANT, RB>(a.w, a.rows, a.n, blockIdx.x, gridDim.x, 4);
+    pdl_wait();
+    matvec_phase<QUANT, EPI, RB, LPG>(a, blockIdx.x, gridDim.x, act, ms);
+    if (EPI == EPI_CLS) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const uint32_t t = atomicAdd(&a.st_rw->cls_ticket, 1u);
+            ms.flag = (t == gridDim.x - 1) ? 1u : 0u;
         }
+        __syncthreads();
+        const bool last = ms.flag != 0;
+        __syncthreads();
+        if (last) { __threadfence(); cls_finalize(a, gridDim.x, ms); }
     }
 }
 
@@ -601,7 +635,7 @@ __global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
-    prep_f32<256>(a.src, a.gain, a.n, true, reinterpret_cast<float *>(act), red);
+    prep_f32<256>(a.src, a.gain, a.n, true, reinterpret_cast<float *>(act), reinterpret_cast<float *>(act) + a.n, red);
     const float *x = reinterpret_cast<const float *>(act);
     const float *W = static_cast<const float *>(a.w);
     const Dims &d = a.d;
@@ -730,29 +764,18 @@ __device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict
 // all KVM query heads of the group; softmax statistics are per-warp (no block barriers); the last CTA of
 // the kv head merges the splits with all threads.
 // smem (floats): qs[KVM*hd] | krow[hd] | sc[KVM*chunk_cap] | wsc[KVM*nsplit_max] | stat[2*KVM] | part[8*rpw*KVM*hd]
-__host__ __device__ inline uint32_t attn_fast_smem_floats(uint32_t kvm, uint32_t hd, uint32_t chunk_cap, uint32_t nsplit_max) {
+__host__ __device__ inline uint32_t attn_fast_smem_floats(uint32_t kvm, uint32_t hd, uint32_t chunk_cap, uint32_t nsplit_max, uint32_t nwarps) {
     uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
     const uint32_t rpw = 32 / lpr;
-    return kvm * hd + hd + kvm * chunk_cap + kvm * nsplit_max + 2 * kvm + 8 + kAttnWarps * rpw * kvm * hd;
+    return kvm * hd + hd + kvm * chunk_cap + kvm * nsplit_max + 2 * kvm + 8 + nwarps * rpw * kvm * hd;
 }
 
-template <int KVM>
-__global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs a) {
-    extern __shared__ __align__(16) float sm[];
-    __shared__ uint32_t is_last;
-    pdl_launch_dependents();
-    pdl_wait();
-
+template <int KVM, int NT>
+__device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_t split, uint32_t pos, uint32_t range, uint32_t chunk,
+                                          uint32_t nsplit, float *sm, uint32_t &is_last) {
+    constexpr int NW = NT / 32;
     const Dims &d = a.d;
     const uint32_t hd = d.hd;
-    const uint32_t g = blockIdx.y, split = blockIdx.x;
-    const uint32_t pos = a.st->pos;
-    const uint32_t range = a.st->is_causal ? pos + 1 : d.max_seq;
-    uint32_t chunk = (range + a.nsplit_max - 1) / a.nsplit_max;
-    chunk = max(chunk, 32u);
-    chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
-    const uint32_t nsplit = (range + chunk - 1) / chunk;
-    if (split >= nsplit) return;
     const uint32_t t0 = split * chunk, t1 = min(range, t0 + chunk), len = t1 - t0;
     const bool owner = (pos >= t0 && pos < t1);
     const uint32_t cap = a.chunk_cap;
@@ -770,16 +793,16 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
     const uint32_t sub = lane / lpr, li = lane % lpr;
     const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
 
-    for (uint32_t i = threadIdx.x; i < KVM * hd; i += kAttnThreads) qs[i] = a.q[(size_t)g * KVM * hd + i];
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) krow[i] = a.kraw[(size_t)g * hd + i];
+    for (uint32_t i = threadIdx.x; i < KVM * hd; i += NT) qs[i] = __ldcg(a.q + (size_t)g * KVM * hd + i);
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) krow[i] = __ldcg(a.kraw + (size_t)g * hd + i);
     __syncthreads();
-    for (uint32_t m = warp; m < KVM + (owner ? 1u : 0u); m += kAttnWarps) {
+    for (uint32_t m = warp; m < KVM + (owner ? 1u : 0u); m += NW) {
         if (m < KVM) head_norm_rope(qs + m * hd, a.qnorm, cr, ci, d, false);
         else head_norm_rope(krow, a.knorm, cr, ci, d, false);
     }
     __syncthreads();
     float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += kAttnThreads) kbase[(size_t)pos * hd + i] = krow[i];
+    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) kbase[(size_t)pos * hd + i] = krow[i];
     const float dv = sqrtf((float)hd);
     const uint32_t col = li * 4;
     const bool colon = col < hd;
@@ -788,13 +811,13 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
     float4 qv[KVM];
 #pragma unroll
     for (int m = 0; m < KVM; m++) qv[m] = colon ? *reinterpret_cast<const float4 *>(qs + m * hd + col) : make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
         const uint32_t tl = tb + sub;
         float4 kv = make_float4(0, 0, 0, 0);
         if (tl < len && colon) {
             const uint32_t t = t0 + tl;
-            const float *kr = (t == pos) ? krow : kbase + (size_t)t * hd;
-            kv = *reinterpret_cast<const float4 *>(kr + col);
+            kv = (t == pos) ? *reinterpret_cast<const float4 *>(krow + col)
+                            : __ldcg(reinterpret_cast<const float4 *>(kbase + (size_t)t * hd + col));
         }
 #pragma unroll
         for (int m = 0; m < KVM; m++) {
@@ -821,10 +844,10 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
     float4 av[KVM];
 #pragma unroll
     for (int m = 0; m < KVM; m++) av[m] = make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += kAttnWarps * rpw) {
+    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
         const uint32_t tl = tb + sub;
         if (tl < len && colon) {
-            const float4 vv = *reinterpret_cast<const float4 *>(vbase + (size_t)(t0 + tl) * hd + col);
+            const float4 vv = __ldcg(reinterpret_cast<const float4 *>(vbase + (size_t)(t0 + tl) * hd + col));
 #pragma unroll
             for (int m = 0; m < KVM; m++) {
                 const float e = sc[m * cap + tl];
@@ -839,8 +862,8 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
             *reinterpret_cast<float4 *>(part + ((size_t)(warp * rpw + sub) * KVM + m) * hd + col) = av[m];
     }
     __syncthreads();
-    const uint32_t np = kAttnWarps * rpw;
-    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += kAttnThreads) {
+    const uint32_t np = NW * rpw;
+    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
         float s = 0.0f;
         for (uint32_t p = 0; p < np; p++) s += part[((size_t)p * KVM + m) * hd + i];
@@ -857,7 +880,7 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
         is_last = (t == nsplit - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return;      // uniform across the CTA
     __threadfence();
     // ---- merge: warp m computes exp(m_s - M) / L for its head; then all threads combine ----
     if (warp < KVM) {
@@ -875,7 +898,7 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
         if (lane == 0) stat[2 * warp] = L;
     }
     __syncthreads();
-    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += kAttnThreads) {
+    for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
         const size_t base = (size_t)(g * KVM + m) * a.nsplit_max;
         float o = 0.0f;
@@ -884,6 +907,24 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
         a.xba[(size_t)(g * KVM + m) * hd + i] = __fdiv_rn(o, stat[2 * m]);
     }
     if (threadIdx.x == 0) a.ticket[g] = 0;
+}
+
+
+template <int KVM>
+__global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ uint32_t is_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    const Dims &d = a.d;
+    const uint32_t pos = __ldcg(&a.st->pos);
+    const uint32_t range = __ldcg(&a.st->is_causal) ? pos + 1 : d.max_seq;
+    uint32_t chunk = (range + a.nsplit_max - 1) / a.nsplit_max;
+    chunk = max(chunk, 32u);
+    chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
+    const uint32_t nsplit = (range + chunk - 1) / chunk;
+    if (blockIdx.x >= nsplit) return;
+    attn_item<KVM, kAttnThreads>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
 }
 
 __global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {
@@ -1135,11 +1176,176 @@ __global__ void __launch_bounds__(kThreads) k_op_prep(const float *src, const fl
                                                      uint32_t exact, float *out_f32, int8_t *dump_codes, float *dump_scales) {
     extern __shared__ __align__(16) unsigned char act[];
     __shared__ float red[32];
+    float *stage = reinterpret_cast<float *>(act + act_region_bytes(quant, n, gs ? gs : 1));
     if (quant == 0x00u) {
-        prep_f32<kThreads>(src, gain, n, exact != 0, reinterpret_cast<float *>(act), red);
+        prep_f32<kThreads>(src, gain, n, exact != 0, reinterpret_cast<float *>(act), stage, red);
         for (uint32_t i = threadIdx.x; i < n; i += kThreads) out_f32[i] = reinterpret_cast<float *>(act)[i];
-    } else if (quant == 0x80u) prep_q80<kThreads>(src, gain, n, gs, exact != 0, act, red, dump_codes, dump_scales);
-    else prep_q4k<kThreads>(src, gain, n, exact != 0, act, red, dump_codes, dump_scales);
+    } else if (quant == 0x80u) prep_q80<kThreads>(src, gain, n, gs, exact != 0, act, stage, red, dump_codes, dump_scales);
+    else prep_q4k<kThreads>(src, gain, n, exact != 0, act, stage, red, dump_codes, dump_scales);
+}
+
+// ================================================================================================
+// Persistent decode megakernel.
+//
+// At batch 1 the path is latency-bound, not bandwidth-bound: a Nano-168M layer is 6.7 MB (~1 us of HBM
+// time) but needs five grid-wide dependencies (QKV -> attention -> O -> W1|W3 -> W2).  Measured on B200,
+// a kernel boundary costs ~6-7 us even inside a CUDA graph with PDL, i.e. ~800 us/token for 122 launches.
+// k_decode_mega keeps one CTA per SM resident for a whole run of tokens and replaces every kernel boundary
+// with a ~1 us counter barrier in L2; while a CTA waits it has already prefetched the next phase's weight
+// rows into L2.  The phases are the same device functions the multi-kernel path launches, so the arithmetic
+// (and the parity results) are identical.
+// ================================================================================================
+struct LayerW {
+    const void *qkv_w, *qkv_aux, *wo_w, *wo_aux, *w13_w, *w13_aux, *w2_w, *w2_aux;
+    const float *g_attn, *g_ffn, *qnorm, *knorm;
+    float *kc, *vc;
+};
+
+struct MegaArgs {
+    const LayerW *layers;               // [L] in HBM (immutable)
+    const void *cls_w, *cls_aux, *emb_w, *emb_aux;
+    const float *g_final, *rope_cos, *rope_sin;
+    float *x, *q, *kraw, *xba, *hb, *logits;
+    float *ws_m, *ws_l, *ws_acc; uint32_t *ticket;
+    DevState *st; uint32_t *ids; uint8_t *seen; float *cls_val; uint32_t *cls_idx;
+    unsigned int *bar;                  // grid barrier counter (zeroed by the host before every launch)
+    uint32_t n_steps, nsplit_max, chunk_cap;
+    int8_t *dump_codes; float *dump_scales;
+    Dims d;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Monotonic counter barrier across the persistent grid (all CTAs co-resident: cooperative launch).
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &target, uint32_t ncta) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += ncta;
+        __threadfence();                                   // release: this CTA's phase outputs
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_u32(ctr) < target) { }
+        __threadfence();                                   // acquire
+    }
+    __syncthreads();
+}
+
+// embedding row -> x (infer.c:987-988 + load-time dequantisation), by one CTA
+template <int NT>
+__device__ __forceinline__ void embed_row(const void *w, const void *aux, float *x, uint32_t tok, const Dims &d) {
+    const uint32_t E = d.E;
+    for (uint32_t i = threadIdx.x; i < E; i += NT) {
+        float v;
+        if (d.quant == 0x00u) v = __ldg(static_cast<const float *>(w) + (size_t)tok * E + i);
+        else if (d.quant == 0x80u) {
+            const int8_t c = __ldg(static_cast<const int8_t *>(w) + (size_t)tok * E + i);
+            const float s = __ldg(static_cast<const float *>(aux) + ((size_t)tok * E + i) / d.gs);
+            v = __fmul_rn((float)c, s);                                  // tensor.c:15-19
+        } else {
+            const uint32_t bpr = E / 256, blk = i >> 8, e = i & 255, g = e >> 5, j = g & 3;
+            const uint8_t byte = __ldg(static_cast<const uint8_t *>(w) + (size_t)tok * (E / 2) + (i >> 1));
+            const uint32_t c = (i & 1) ? (byte >> 4) : (byte & 0x0f);
+            const uint32_t *rec = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(aux) + ((size_t)tok * bpr + blk) * 20);
+            const float ss = __uint_as_float(__ldg(rec)), sbi = __uint_as_float(__ldg(rec + 1));
+            const uint32_t bs = (__ldg(rec + 2) >> (8 * j)) & 0xff, bb = (__ldg(rec + 3) >> (8 * j)) & 0xff, bh = (__ldg(rec + 4) >> (8 * j)) & 0xff;
+            const uint32_t s6 = (g < 4) ? (bs & 0x3f) : ((((bs >> 6) << 4) | (bh & 0x0f)) & 0x3f);
+            const uint32_t b6 = (g < 4) ? (bb & 0x3f) : ((((bb >> 6) << 4) | (bh >> 4)) & 0x3f);
+            v = __fsub_rn(__fmul_rn((float)c, __fmul_rn((float)s6, ss)), __fmul_rn((float)b6, sbi));   // tensor.c:274
+        }
+        x[i] = v;
+    }
+}
+
+template <int QUANT, int LPG, int KVM>
+__global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ MatvecSmem ms;
+    __shared__ uint32_t attn_flag;
+    constexpr int RBL = 2, RBC = 4;                 // rows per warp task: layer matrices / classifier
+    const uint32_t cta = blockIdx.x, ncta = gridDim.x;
+    const Dims &d = g.d;
+    unsigned int target = 0;
+
+    if (cta == 0) {
+        const uint32_t p0 = __ldcg(&g.st->pos);
+        const uint32_t tok = __ldcg(&g.st->use_token) ? __ldcg(&g.st->token) : __ldcg(g.ids + p0);
+        embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, tok, d);
+    }
+    prefetch_row_blocks<QUANT, RBL>(g.layers[0].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
+    grid_barrier(g.bar, target, ncta);
+
+    for (uint32_t step = 0; step < g.n_steps; step++) {
+        const uint32_t pos = __ldcg(&g.st->pos);
+        const uint32_t range = __ldcg(&g.st->is_causal) ? pos + 1 : d.max_seq;
+        uint32_t chunk = (range + g.nsplit_max - 1) / g.nsplit_max;
+        chunk = max(chunk, 32u);
+        chunk = min((chunk + 7u) & ~7u, g.chunk_cap);
+        const uint32_t nsplit = (range + chunk - 1) / chunk;
+
+        for (uint32_t l = 0; l < d.L; l++) {
+            const LayerW &lw = g.layers[l];
+            MatvecArgs a{};
+            a.d = d; a.st = g.st;
+            // ---- P1: rmsnorm + quantise + QKV + V store ----
+            a.w = lw.qkv_w; a.w_aux = lw.qkv_aux; a.rows = d.q_dim + 2 * d.kv_dim; a.n = d.E;
+            a.src = g.x; a.gain = lw.g_attn; a.out = g.q; a.out_k = g.kraw; a.out_v = lw.vc;
+            a.dump_codes = g.dump_codes; a.dump_scales = g.dump_scales;
+            matvec_phase<QUANT, EPI_QKV, RBL, LPG>(a, cta, ncta, dsm, ms);
+            prefetch_row_blocks<QUANT, RBL>(lw.wo_w, d.E, d.q_dim, cta, ncta, 4);
+            grid_barrier(g.bar, target, ncta);
+            // ---- P2: attention over (kv head, split) items ----
+            {
+                AttnArgs t{};
+                t.q = g.q; t.kraw = g.kraw; t.kc = lw.kc; t.vc = lw.vc; t.qnorm = lw.qnorm; t.knorm = lw.knorm;
+                t.rope_cos = g.rope_cos; t.rope_sin = g.rope_sin; t.xba = g.xba;
+                t.ws_m = g.ws_m; t.ws_l = g.ws_l; t.ws_acc = g.ws_acc; t.ticket = g.ticket; t.st = g.st;
+                t.nsplit_max = g.nsplit_max; t.chunk_cap = g.chunk_cap; t.d = d;
+                for (uint32_t item = cta; item < d.KV * nsplit; item += ncta) {
+                    attn_item<KVM, kThreads>(t, item / nsplit, item % nsplit, pos, range, chunk, nsplit, reinterpret_cast<float *>(dsm), attn_flag);
+                    __syncthreads();
+                }
+            }
+            prefetch_row_blocks<QUANT, RBL>(lw.w13_w, 2 * d.F, d.E, cta, ncta, 4);
+            grid_barrier(g.bar, target, ncta);
+            // ---- P3: quantise(xba) + O + residual ----
+            a.w = lw.wo_w; a.w_aux = lw.wo_aux; a.rows = d.E; a.n = d.q_dim;
+            a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr;
+            matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
+            grid_barrier(g.bar, target, ncta);
+            // ---- P4: rmsnorm + quantise + W1|W3 + SwiGLU ----
+            a.w = lw.w13_w; a.w_aux = lw.w13_aux; a.rows = 2 * d.F; a.n = d.E;
+            a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb;
+            matvec_phase<QUANT, EPI_SWIGLU, RBL, LPG>(a, cta, ncta, dsm, ms);
+            prefetch_row_blocks<QUANT, RBL>(lw.w2_w, d.E, d.F, cta, ncta, 4);
+            grid_barrier(g.bar, target, ncta);
+            // ---- P5: quantise(hb) + W2 + residual ----
+            a.w = lw.w2_w; a.w_aux = lw.w2_aux; a.rows = d.E; a.n = d.F;
+            a.src = g.hb; a.gain = nullptr; a.out = g.x;
+            matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
+            if (l + 1 < d.L) prefetch_row_blocks<QUANT, RBL>(g.layers[l + 1].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
+            else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 2);
+            grid_barrier(g.bar, target, ncta);
+        }
+        // ---- classifier: final rmsnorm + quantise + matvec + penalty + per-CTA argmax ----
+        {
+            MatvecArgs a{};
+            a.d = d; a.st = g.st; a.st_rw = g.st;
+            a.w = g.cls_w; a.w_aux = g.cls_aux; a.rows = d.V; a.n = d.E;
+            a.src = g.x; a.gain = g.g_final; a.out = g.logits;
+            a.seen = g.seen; a.seen_rw = g.seen; a.cls_val = g.cls_val; a.cls_idx = g.cls_idx; a.ids = g.ids;
+            matvec_phase<QUANT, EPI_CLS, RBC, LPG>(a, cta, ncta, dsm, ms);
+            prefetch_row_blocks<QUANT, RBL>(g.layers[0].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
+            grid_barrier(g.bar, target, ncta);
+            if (cta == 0) {
+                const uint32_t nxt = cls_finalize(a, ncta, ms);
+                if (step + 1 < g.n_steps) embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, nxt, d);
+            }
+            grid_barrier(g.bar, target, ncta);
+        }
+    }
 }
 
 }  // namespace nb

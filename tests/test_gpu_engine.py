@@ -64,8 +64,9 @@ def reference_noise_floor(name, quant, gs, path, S):
     return floor
 
 
+@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_MEGA], ids=["megakernel", "multikernel"])
 @pytest.mark.parametrize("name,quant,gs", TOY)
-def test_teacher_forced_logits_fast_mode(name, quant, gs):
+def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags):
     """Fast mode (parallel fp32 reductions): within the north-star tolerance, or -- where the reference's own
     -O3 -ffast-math build already deviates more than that from its strict build on the same file (a 1-ulp
     upstream difference flips an int8/uint4 activation code) -- within 1.5x that measured noise floor.
@@ -73,7 +74,7 @@ def test_teacher_forced_logits_fast_mode(name, quant, gs):
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S = 40
-    eng = E.Engine(path, S); o = ob.NanoOracle(path, S)
+    eng = E.Engine(path, S, flags=path_flags); o = ob.NanoOracle(path, S)
     toks = mf.teacher_tokens(S, spec.vocab)
     floor = reference_noise_floor(name, quant, gs, path, S)
     limit = max(TOL[quant], 1.5 * floor)
@@ -165,15 +166,21 @@ def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty):
         eng.decode_greedy(ids2, P, S, penalty)
         assert ids2[:S].tolist() == ids_o[:S].tolist()
         eng.close()
-    # fast mode: device loop == API loop (same kernels, same order)
-    eng = E.Engine(path, S)
-    a = np.zeros(S + 1, np.uint32); a[:P] = prompt
-    for pos in range(S - 1):
-        a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
-    b = np.zeros(S + 1, np.uint32); b[:P] = prompt
-    eng.decode_greedy(b, P, S, penalty)
-    assert a[:S].tolist() == b[:S].tolist()
-    eng.close(); o.close()
+    # fast mode: device loop == API loop, and persistent megakernel == multi-kernel graph (same phase code)
+    runs = []
+    for flags in (0, E.FLAG_NO_MEGA):
+        eng = E.Engine(path, S, flags=flags)
+        a = np.zeros(S + 1, np.uint32); a[:P] = prompt
+        for pos in range(S - 1):
+            a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
+        b = np.zeros(S + 1, np.uint32); b[:P] = prompt
+        eng.decode_greedy(b, P, S, penalty)
+        assert a[:S].tolist() == b[:S].tolist()
+        runs.append((a[:S].tolist(), eng.logits()))
+        eng.close()
+    assert runs[0][0] == runs[1][0]
+    assert_bits_equal(runs[0][1], runs[1][1], "megakernel vs multi-kernel logits")
+    o.close()
 
 
 def test_activation_codes_dump_bit_exact():
