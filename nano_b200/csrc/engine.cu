@@ -629,7 +629,7 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) mk = nullptr;
-    uint32_t nsm = mk ? (uint32_t)e->num_sms / d.KV : (uint32_t)(2 * e->num_sms + d.KV - 1) / d.KV;
+    uint32_t nsm = (uint32_t)e->num_sms / d.KV;     // (kv head, split) items <= one per SM; same split in both paths => identical bits
     if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
     e->nsplit_max = nsm;
     uint32_t cap = (d.max_seq + nsm - 1) / nsm; cap = (cap + 7u) & ~7u; if (cap < 32) cap = 32;

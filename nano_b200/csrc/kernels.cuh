@@ -129,8 +129,14 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // CTAs (another kernel, or another phase of the persistent kernel), so it must not come from L1 / the
 // non-coherent path.
 template <int NT>
-__device__ __forceinline__ void stage_vector(const float *src, int n, float *stage) {
-    for (int i = threadIdx.x; i < n; i += NT) stage[i] = __ldcg(src + i);
+__device__ __forceinline__ void stage_vector(const float *src, const float *__restrict__ gain, int n, float *stage) {
+    float *gstage = stage + n;                       // the rmsnorm gain rides along (one L2 latency, not two)
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const float v = __ldcg(src + i);
+        const float g = gain ? __ldg(gain + i) : 0.0f;
+        stage[i] = v;
+        if (gain) gstage[i] = g;
+    }
     __syncthreads();
 }
 
@@ -157,14 +163,14 @@ __device__ __forceinline__ float rms_inverse(const float *stage, int n, bool exa
     return __fdiv_rn(1.0f, __fsqrt_rn(ss));
 }
 
-__device__ __forceinline__ float act_value(const float *stage, const float *__restrict__ gain, float inv, int i) {
+__device__ __forceinline__ float act_value(const float *stage, int n, bool has_gain, float inv, int i) {
     const float v = stage[i];
-    return gain ? __fmul_rn(__ldg(gain + i), __fmul_rn(inv, v)) : v;
+    return has_gain ? __fmul_rn(stage[n + i], __fmul_rn(inv, v)) : v;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Activation preparation into shared memory (each CTA redoes it: <= 39 KB of L2 reads, no grid sync)
-// smem layouts (followed by the fp32 staging copy of the source, n floats):
+// smem layouts (followed by fp32 staging copies of the source and of the rmsnorm gain, n floats each):
 //   F32 : float v[n]
 //   Q80 : int8 codes[n] | pad16 | float scales[n/gs]
 //   Q4K : u32 xe[n/8] (even elements) | u32 xo[n/8] (odd elements) | float4 {sq,bq,sum_q,0}[n/32]
@@ -177,15 +183,15 @@ __host__ __device__ inline uint32_t act_region_bytes(uint32_t quant, uint32_t n,
     return (b + 15u) & ~15u;
 }
 __host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, uint32_t gs) {
-    return act_region_bytes(quant, n, gs) + n * 4u;      // + staging copy
+    return act_region_bytes(quant, n, gs) + 2u * n * 4u;      // + staging copies of the source and the gain
 }
 
 template <int NT>
 __device__ void prep_f32(const float *src, const float *__restrict__ gain, int n, bool exact, float *act, float *stage, float *red) {
-    stage_vector<NT>(src, n, stage);
+    stage_vector<NT>(src, gain, n, stage);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
-    for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(stage, gain, inv, i);
+    for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(stage, n, gain != nullptr, inv, i);
     __syncthreads();
 }
 
@@ -195,7 +201,7 @@ __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n
                          unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales) {
     int8_t *codes = reinterpret_cast<int8_t *>(act);
     float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
-    stage_vector<NT>(src, n, stage);
+    stage_vector<NT>(src, gain, n, stage);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,7 +212,7 @@ __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n
         const int base = g * gs + lane * epl;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (j < epl) { v[j] = act_value(stage, gain, inv, base + j); amax = fmaxf(amax, fabsf(v[j])); }
+            if (j < epl) { v[j] = act_value(stage, n, gain != nullptr, inv, base + j); amax = fmaxf(amax, fabsf(v[j])); }
         }
         amax = warp_max(amax);
         const float sc = __fdiv_rn(amax, 127.0f);
@@ -237,7 +243,7 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
     uint32_t *xe = reinterpret_cast<uint32_t *>(act);
     uint32_t *xo = reinterpret_cast<uint32_t *>(act + n / 2);
     float4 *gp = reinterpret_cast<float4 *>(act + n);
-    stage_vector<NT>(src, n, stage);
+    stage_vector<NT>(src, gain, n, stage);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,7 +255,7 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
         const int base = b * 256 + lane * 8;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            v[j] = act_value(stage, gain, inv, base + j);
+            v[j] = act_value(stage, n, gain != nullptr, inv, base + j);
             if (v[j] > hi) hi = v[j];
             if (v[j] < lo) lo = v[j];
         }
@@ -302,56 +308,73 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
 // ------------------------------------------------------------------------------------------------
 
 // matmul_quant, infer.c:654-679.  LPG = lanes per quantisation group = gs/16.
+// A tile is the weight codes + scales of one macro-step (2 x 512 bytes) of RB rows, held in registers so that
+// it can be requested from HBM/L2 BEFORE the activation prologue (weights never depend on activations).
+template <int RB>
+struct Q80Tile { int4 w[2][RB]; float ws[2][RB]; };
+
 template <int RB, int LPG>
-__device__ __forceinline__ void rows_q80(const int8_t *__restrict__ W, const float *__restrict__ S, uint32_t row0,
-                                         uint32_t rows, uint32_t n, const unsigned char *act, float *val) {
+__device__ __forceinline__ void q80_load(Q80Tile<RB> &t, const int8_t *__restrict__ W, const float *__restrict__ S, uint32_t row0,
+                                         uint32_t rows, uint32_t n, uint32_t k0) {
     constexpr uint32_t gs = LPG * 16;
+    const int lane = threadIdx.x & 31;
+    const uint32_t G = n / gs;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const uint32_t k = k0 + s * 512 + lane * 16;
+        const bool on = k < n;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const uint32_t row = min(row0 + r, rows - 1);
+            t.w[s][r] = on ? ldg_stream16(W + (size_t)row * n + k) : make_int4(0, 0, 0, 0);
+            t.ws[s][r] = on ? __ldg(S + (size_t)row * G + k / gs) : 0.0f;
+        }
+    }
+}
+
+template <int RB, int LPG>
+__device__ __forceinline__ void q80_consume(const Q80Tile<RB> &t, uint32_t n, uint32_t k0, const unsigned char *act, float *val) {
+    constexpr uint32_t gs = LPG * 16;
+    constexpr int GPS = 32 / LPG;   // groups covered by one 512-byte step
     const int lane = threadIdx.x & 31;
     const int8_t *codes = reinterpret_cast<const int8_t *>(act);
     const float *xs = reinterpret_cast<const float *>(act + ((n + 15) & ~15));
-    const uint32_t G = n / gs;
-    constexpr int GPS = 32 / LPG;   // groups covered by one 512-byte step
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const uint32_t kbase = k0 + s * 512;
+        if (kbase >= n) break;
+        const uint32_t k = kbase + lane * 16;
+        const bool on = k < n;
+        const int4 xq = on ? *reinterpret_cast<const int4 *>(codes + k) : make_int4(0, 0, 0, 0);
+        const float xsc = on ? xs[k / gs] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            int isum = __dp4a(t.w[s][r].x, xq.x, 0);
+            isum = __dp4a(t.w[s][r].y, xq.y, isum);
+            isum = __dp4a(t.w[s][r].z, xq.z, isum);
+            isum = __dp4a(t.w[s][r].w, xq.w, isum);
+#pragma unroll
+            for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+            const float term = __fmul_rn(__fmul_rn((float)isum, t.ws[s][r]), xsc);
+#pragma unroll
+            for (int g = 0; g < GPS; g++) {
+                const float v = __shfl_sync(0xffffffffu, term, g * LPG);
+                if (kbase + g * gs < n) val[r] = __fadd_rn(val[r], v);
+            }
+        }
+    }
+}
+
+template <int RB, int LPG>
+__device__ __forceinline__ void rows_q80(const int8_t *__restrict__ W, const float *__restrict__ S, uint32_t row0,
+                                         uint32_t rows, uint32_t n, const unsigned char *act, float *val, const Q80Tile<RB> *pre) {
 #pragma unroll
     for (int r = 0; r < RB; r++) val[r] = 0.0f;
     for (uint32_t k0 = 0; k0 < n; k0 += 1024) {
-        // ---- issue all loads of two steps first (memory-level parallelism) ----
-        int4 w[2][RB];
-        float ws[2][RB];
-        int4 xq[2];
-        float xsc[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const uint32_t k = k0 + s * 512 + lane * 16;
-            const bool on = k < n;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const uint32_t row = min(row0 + r, rows - 1);
-                w[s][r] = on ? ldg_stream16(W + (size_t)row * n + k) : make_int4(0, 0, 0, 0);
-                ws[s][r] = on ? __ldg(S + (size_t)row * G + k / gs) : 0.0f;
-            }
-            xq[s] = on ? *reinterpret_cast<const int4 *>(codes + k) : make_int4(0, 0, 0, 0);
-            xsc[s] = on ? xs[k / gs] : 0.0f;
-        }
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const uint32_t kbase = k0 + s * 512;
-            if (kbase >= n) break;
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                int isum = __dp4a(w[s][r].x, xq[s].x, 0);
-                isum = __dp4a(w[s][r].y, xq[s].y, isum);
-                isum = __dp4a(w[s][r].z, xq[s].z, isum);
-                isum = __dp4a(w[s][r].w, xq[s].w, isum);
-#pragma unroll
-                for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
-                const float term = __fmul_rn(__fmul_rn((float)isum, ws[s][r]), xsc[s]);
-#pragma unroll
-                for (int g = 0; g < GPS; g++) {
-                    const float t = __shfl_sync(0xffffffffu, term, g * LPG);
-                    if (kbase + g * gs < n) val[r] = __fadd_rn(val[r], t);
-                }
-            }
-        }
+        Q80Tile<RB> t;
+        if (k0 == 0 && pre) t = *pre;
+        else q80_load<RB, LPG>(t, W, S, row0, rows, n, k0);
+        q80_consume<RB, LPG>(t, n, k0, act, val);
     }
 }
 
@@ -477,7 +500,8 @@ struct MatvecSmem {
 // Weights never depend on activations: pull a warp's first row blocks of a matrix towards L2 ahead of time
 // (before the PDL wait / before a grid barrier), so the HBM latency hides behind the wait.
 template <int QUANT, int RB>
-__device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows, uint32_t n, uint32_t cta, uint32_t ncta, uint32_t max_iters) {
+__device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows, uint32_t n, uint32_t cta, uint32_t ncta, uint32_t max_iters,
+                                                    const void *aux = nullptr, uint32_t aux_row_bytes = 0, const float *gain = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblocks = (rows + RB - 1) / RB;
     const uint32_t gwarp = cta * kWarps + warp, nwarps = ncta * kWarps;
@@ -487,7 +511,12 @@ __device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows
     for (uint32_t rb = gwarp; rb < nblocks && it < max_iters; rb += nwarps, it++) {
         const char *base = static_cast<const char *>(w) + (size_t)rb * blkbytes;
         for (uint32_t off = lane * 128u; off < blkbytes; off += 32u * 128u) prefetch_l2(base + off);
+        if (aux) {
+            const char *ab = static_cast<const char *>(aux) + (size_t)rb * RB * aux_row_bytes;
+            for (uint32_t off = lane * 128u; off < RB * aux_row_bytes; off += 32u * 128u) prefetch_l2(ab + off);
+        }
     }
+    if (gain && warp == 0) for (uint32_t off = (cta * 32u + lane) * 32u; off < n; off += ncta * 32u * 32u) prefetch_l2(gain + off);
 }
 
 template <int QUANT, int EPI, int RB, int LPG>
@@ -498,6 +527,17 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     const uint32_t nblocks = (a.rows + RB - 1) / RB;
     const uint32_t gwarp = cta * kWarps + warp, nwarps = ncta * kWarps;
     float *stage = reinterpret_cast<float *>(act + act_region_bytes(QUANT, a.n, (QUANT == 0x80) ? LPG * 16 : 1));
+
+    // request this warp's first weight tile (and the residual it will add to) before the activation prologue
+    Q80Tile<RB> pre;
+    float xres[RB];
+    const bool has_first = gwarp < nblocks;
+    if (QUANT == 0x80 && has_first)
+        q80_load<RB, LPG>(pre, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), gwarp * RB, a.rows, a.n, 0);
+    if (EPI == EPI_RESID && has_first) {
+#pragma unroll
+        for (int r = 0; r < RB; r++) xres[r] = __ldcg(a.out + min(gwarp * RB + r, a.rows - 1));
+    }
 
     if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red);
     else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
@@ -512,7 +552,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
         const uint32_t row0 = rb * RB;
         float val[RB];
         if (QUANT == 0x00) rows_f32<RB>(static_cast<const float *>(a.w), row0, a.rows, a.n, act, val);
-        else if (QUANT == 0x80) rows_q80<RB, LPG>(static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, act, val);
+        else if (QUANT == 0x80) rows_q80<RB, LPG>(static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, act, val, rb == gwarp ? &pre : nullptr);
         else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
 
         if (EPI == EPI_SWIGLU) {
@@ -533,7 +573,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 if (row >= a.rows) break;
                 float v = val[r];
                 if (EPI == EPI_STORE) { if (lane == 0) a.out[row] = v; }
-                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(__ldcg(a.out + row), v); }
+                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(rb == gwarp ? xres[r] : __ldcg(a.out + row), v); }
                 else if (EPI == EPI_QKV) {
                     if (lane == 0) {
                         if (row < d.q_dim) a.out[row] = v;
@@ -545,7 +585,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                     }
                 } else if (EPI == EPI_CLS) {
                     // infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037
-                    if (pen != 1.0f && a.seen[row]) v = __fdiv_rn(v, pen);      // x / 1.0f == x: skip the lookup
+                    if (pen != 1.0f && __ldcg(a.seen + row)) v = __fdiv_rn(v, pen);      // x / 1.0f == x: skip the lookup
                     if (lane == 0) a.out[row] = v;
                     if (v > bestv) { bestv = v; besti = row; }
                 }
@@ -635,7 +675,7 @@ __global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
-    prep_f32<256>(a.src, a.gain, a.n, true, reinterpret_cast<float *>(act), reinterpret_cast<float *>(act) + a.n, red);
+    prep_f32<256>(a.src, a.gain, a.n, true, reinterpret_cast<float *>(act), reinterpret_cast<float *>(act) + a.n, red);   // smem: 3n floats
     const float *x = reinterpret_cast<const float *>(act);
     const float *W = static_cast<const float *>(a.w);
     const Dims &d = a.d;
@@ -1225,10 +1265,8 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &ta
     __syncthreads();
     if (threadIdx.x == 0) {
         target += ncta;
-        __threadfence();                                   // release: this CTA's phase outputs
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");   // release: this CTA's phase outputs
         while (ld_acquire_u32(ctr) < target) { }
-        __threadfence();                                   // acquire
     }
     __syncthreads();
 }
@@ -1274,7 +1312,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
         const uint32_t tok = __ldcg(&g.st->use_token) ? __ldcg(&g.st->token) : __ldcg(g.ids + p0);
         embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, tok, d);
     }
-    prefetch_row_blocks<QUANT, RBL>(g.layers[0].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
+    // L2 prefetch of a later phase's weight rows (+ scales / side records, + rmsnorm gain), issued before a barrier
+    auto pf = [&](const void *w, const void *aux, uint32_t rows, uint32_t n, const float *gain) {
+        const uint32_t arb = (QUANT == 0x80) ? (n / (LPG * 16u)) * 4u : (QUANT == 0x42) ? (n / 256u) * 20u : 0u;
+        prefetch_row_blocks<QUANT, RBL>(w, rows, n, cta, ncta, 8, aux, arb, gain);
+    };
+    pf(g.layers[0].qkv_w, g.layers[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[0].g_attn);
     grid_barrier(g.bar, target, ncta);
 
     for (uint32_t step = 0; step < g.n_steps; step++) {
@@ -1294,7 +1337,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
             a.src = g.x; a.gain = lw.g_attn; a.out = g.q; a.out_k = g.kraw; a.out_v = lw.vc;
             a.dump_codes = g.dump_codes; a.dump_scales = g.dump_scales;
             matvec_phase<QUANT, EPI_QKV, RBL, LPG>(a, cta, ncta, dsm, ms);
-            prefetch_row_blocks<QUANT, RBL>(lw.wo_w, d.E, d.q_dim, cta, ncta, 4);
+            pf(lw.wo_w, lw.wo_aux, d.E, d.q_dim, nullptr);
+            if (cta < d.KV * nsplit) {          // the K/V chunk of this CTA's attention item (old rows: already final)
+                const uint32_t ag = cta / nsplit, as = cta % nsplit;
+                const uint32_t t0 = as * chunk, t1 = min(range, t0 + chunk);
+                const char *kb = reinterpret_cast<const char *>(lw.kc + ((size_t)ag * d.max_seq + t0) * d.hd);
+                const char *vb = reinterpret_cast<const char *>(lw.vc + ((size_t)ag * d.max_seq + t0) * d.hd);
+                const uint32_t bytes = (t1 - t0) * d.hd * 4u;
+                for (uint32_t off = threadIdx.x * 128u; off < bytes; off += kThreads * 128u) { prefetch_l2(kb + off); prefetch_l2(vb + off); }
+            }
             grid_barrier(g.bar, target, ncta);
             // ---- P2: attention over (kv head, split) items ----
             {
@@ -1308,25 +1359,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
                     __syncthreads();
                 }
             }
-            prefetch_row_blocks<QUANT, RBL>(lw.w13_w, 2 * d.F, d.E, cta, ncta, 4);
+            pf(lw.w13_w, lw.w13_aux, 2 * d.F, d.E, lw.g_ffn);
             grid_barrier(g.bar, target, ncta);
             // ---- P3: quantise(xba) + O + residual ----
             a.w = lw.wo_w; a.w_aux = lw.wo_aux; a.rows = d.E; a.n = d.q_dim;
             a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr;
             matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
+            pf(lw.w2_w, lw.w2_aux, d.E, d.F, nullptr);
             grid_barrier(g.bar, target, ncta);
             // ---- P4: rmsnorm + quantise + W1|W3 + SwiGLU ----
             a.w = lw.w13_w; a.w_aux = lw.w13_aux; a.rows = 2 * d.F; a.n = d.E;
             a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb;
             matvec_phase<QUANT, EPI_SWIGLU, RBL, LPG>(a, cta, ncta, dsm, ms);
-            prefetch_row_blocks<QUANT, RBL>(lw.w2_w, d.E, d.F, cta, ncta, 4);
+            if (l + 1 < d.L) pf(g.layers[l + 1].qkv_w, g.layers[l + 1].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[l + 1].g_attn);
+            else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 4, nullptr, 0, g.g_final);
             grid_barrier(g.bar, target, ncta);
             // ---- P5: quantise(hb) + W2 + residual ----
             a.w = lw.w2_w; a.w_aux = lw.w2_aux; a.rows = d.E; a.n = d.F;
             a.src = g.hb; a.gain = nullptr; a.out = g.x;
             matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
-            if (l + 1 < d.L) prefetch_row_blocks<QUANT, RBL>(g.layers[l + 1].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
-            else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 2);
             grid_barrier(g.bar, target, ncta);
         }
         // ---- classifier: final rmsnorm + quantise + matvec + penalty + per-CTA argmax ----
@@ -1337,7 +1388,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
             a.src = g.x; a.gain = g.g_final; a.out = g.logits;
             a.seen = g.seen; a.seen_rw = g.seen; a.cls_val = g.cls_val; a.cls_idx = g.cls_idx; a.ids = g.ids;
             matvec_phase<QUANT, EPI_CLS, RBC, LPG>(a, cta, ncta, dsm, ms);
-            prefetch_row_blocks<QUANT, RBL>(g.layers[0].qkv_w, d.q_dim + 2 * d.kv_dim, d.E, cta, ncta, 4);
+            pf(g.layers[0].qkv_w, g.layers[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[0].g_attn);
             grid_barrier(g.bar, target, ncta);
             if (cta == 0) {
                 const uint32_t nxt = cls_finalize(a, ncta, ms);
