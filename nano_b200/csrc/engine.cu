@@ -99,7 +99,8 @@ struct nb200_engine {
     cudaGraphExec_t graph = nullptr;
     bool use_pdl = true;
     // persistent megakernel (fast mode): one cooperative launch runs n tokens
-    bool use_mega = false; const void *mega_kern = nullptr; uint32_t mega_smem = 0; LayerW *layers_dev = nullptr; unsigned int *bar = nullptr;
+    unsigned long long *trace_dev = nullptr;
+    bool use_mega = false; const void *mega_kern = nullptr; uint32_t mega_smem = 0, mega_phase_smem = 0; LayerW *layers_dev = nullptr; unsigned int *bar = nullptr;
     uint64_t launches = 0, weight_bytes = 0;
     uint32_t launches_per_token = 0;
     std::vector<uint32_t> seen_mirror;   // ids whose seen[] flag is set, by position
@@ -262,9 +263,9 @@ int run_layer(nb200_engine *e, uint32_t l) {
                 case 8: kern = k_attention_fast<8>; break;
                 default: break;
             }
-            if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kAttnWarps) * 4u;
+            if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kWarps) * 4u;
         }
-        if ((r = launch<AttnArgs>(e, kern, dim3(e->nsplit_max, d.KV), dim3(kAttnThreads), smem, a))) return r;
+        if ((r = launch<AttnArgs>(e, kern, dim3(e->nsplit_max, d.KV), dim3(kern != k_attention ? kThreads : kAttnThreads), smem, a))) return r;
     } else {
         AttnExactArgs a{};
         a.q = e->q; a.kraw = e->kraw; a.kc = e->kc + l * kvl; a.vc = e->vc + l * kvl;
@@ -347,6 +348,7 @@ int launch_mega(nb200_engine *e, uint32_t n_steps) {
     g.ws_m = e->ws_m; g.ws_l = e->ws_l; g.ws_acc = e->ws_acc; g.ticket = e->tickets;
     g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.cls_val = e->cls_val; g.cls_idx = e->cls_idx;
     g.bar = e->bar; g.n_steps = n_steps; g.nsplit_max = e->nsplit_max; g.chunk_cap = e->chunk_cap;
+    g.phase_smem = e->mega_phase_smem; g.trace = e->trace_dev;
     g.dump_codes = e->dump_codes; g.dump_scales = e->dump_scales; g.d = e->d;
     CK(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), e->stream));
     void *params[] = {&g};
@@ -657,6 +659,9 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
         uint32_t sm = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kWarps) * 4u;
         const uint32_t ns[3] = {d.E, d.q_dim, d.F};
         for (uint32_t n : ns) { const uint32_t b = act_smem_bytes(d.quant, n, d.gs ? d.gs : 1); if (b > sm) sm = b; }
+        sm = (sm + 15u) & ~15u;
+        e->mega_phase_smem = sm;
+        sm += (uint32_t)(L * sizeof(LayerW));
         int occ = 0;
         cudaError_t ce = cudaFuncSetAttribute((const void *)mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)mk, kThreads, sm);
@@ -872,6 +877,26 @@ int nb200_profile_tokens(nb200_engine *e, const uint32_t *ids, uint32_t start, u
         cudaEventDestroy(p.a); cudaEventDestroy(p.b);
     }
     e->prof.clear();
+    return r;
+}
+
+// Debug: per-barrier clock64() stamps of CTA 0 for one token through the persistent kernel (5L+3 stamps + 1).
+int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned long long *stamps, uint32_t cap, uint32_t *count) {
+    if (!e || !stamps || !count) return fail(NB200_EINVAL, "null argument");
+    if (!e->use_mega) return fail(NB200_EINVAL, "persistent kernel not active");
+    CK(cudaSetDevice(e->device));
+    const uint32_t n = 5 * e->d.L + 4;
+    if (cap < n) return fail(NB200_EINVAL, "need room for %u stamps", n);
+    unsigned long long *buf = nullptr;
+    CK(cudaMalloc(&buf, (size_t)n * 8));
+    CK(cudaMemset(buf, 0, (size_t)n * 8));
+    e->trace_dev = buf;
+    int r = push_state(e, pos, 1, 0, 0, 1.0f, token, 1);
+    if (!r) r = launch_mega(e, 1);
+    e->trace_dev = nullptr;
+    cudaStreamSynchronize(e->stream);
+    if (!r) { CK(cudaMemcpy(stamps, buf, (size_t)n * 8, cudaMemcpyDeviceToHost)); *count = n; }
+    cudaFree(buf);
     return r;
 }
 

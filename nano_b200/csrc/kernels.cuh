@@ -71,6 +71,8 @@ struct MatvecArgs {
     uint32_t *ids;          // device copy of output_ids
     // debug dump of the prepared activation (written by CTA 0 when non-null)
     int8_t *dump_codes; float *dump_scales;
+    // persistent kernel: step state already in registers (saves an L2 round trip per phase)
+    uint32_t state_known, pos_val; float pen_val;
     Dims d;
 };
 
@@ -543,10 +545,10 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
     else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
 
-    const uint32_t pos = a.st ? __ldcg(&a.st->pos) : 0;
+    const uint32_t pos = a.state_known ? a.pos_val : (a.st ? __ldcg(&a.st->pos) : 0);
     float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
     float pen = 1.0f;
-    if (EPI == EPI_CLS) pen = __ldcg(&a.st->penalty);
+    if (EPI == EPI_CLS) pen = a.state_known ? a.pen_val : __ldcg(&a.st->penalty);
 
     for (uint32_t rb = gwarp; rb < nblocks; rb += nwarps) {
         const uint32_t row0 = rb * RB;
@@ -951,7 +953,7 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
 
 
 template <int KVM>
-__global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs a) {
+__global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {      // same CTA shape as the megakernel => same bits
     extern __shared__ __align__(16) float sm[];
     __shared__ uint32_t is_last;
     pdl_launch_dependents();
@@ -964,7 +966,7 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_fast(const AttnArgs 
     chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
     const uint32_t nsplit = (range + chunk - 1) / chunk;
     if (blockIdx.x >= nsplit) return;
-    attn_item<KVM, kAttnThreads>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
+    attn_item<KVM, kThreads>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
 }
 
 __global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {
@@ -1250,6 +1252,8 @@ struct MegaArgs {
     DevState *st; uint32_t *ids; uint8_t *seen; float *cls_val; uint32_t *cls_idx;
     unsigned int *bar;                  // grid barrier counter (zeroed by the host before every launch)
     uint32_t n_steps, nsplit_max, chunk_cap;
+    uint32_t phase_smem;                // bytes of dynamic smem used by the phases; the layer table follows
+    unsigned long long *trace;          // optional: CTA 0 stamps clock64() after every barrier of the LAST step
     int8_t *dump_codes; float *dump_scales;
     Dims d;
 };
@@ -1307,6 +1311,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
     const Dims &d = g.d;
     unsigned int target = 0;
 
+    // The per-layer pointer table lives in shared memory: every grid barrier invalidates L1 (CCTL.IVALL), so a
+    // table left in HBM costs a chain of dependent L2 round trips at the start of every phase.
+    LayerW *lws = reinterpret_cast<LayerW *>(dsm + g.phase_smem);
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(g.layers);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(lws);
+        for (uint32_t i = threadIdx.x; i < d.L * (uint32_t)(sizeof(LayerW) / 8); i += kThreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
     if (cta == 0) {
         const uint32_t p0 = __ldcg(&g.st->pos);
         const uint32_t tok = __ldcg(&g.st->use_token) ? __ldcg(&g.st->token) : __ldcg(g.ids + p0);
@@ -1317,11 +1331,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
         const uint32_t arb = (QUANT == 0x80) ? (n / (LPG * 16u)) * 4u : (QUANT == 0x42) ? (n / 256u) * 20u : 0u;
         prefetch_row_blocks<QUANT, RBL>(w, rows, n, cta, ncta, 8, aux, arb, gain);
     };
-    pf(g.layers[0].qkv_w, g.layers[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[0].g_attn);
+    pf(lws[0].qkv_w, lws[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[0].g_attn);
     grid_barrier(g.bar, target, ncta);
 
+    uint32_t ti = 0;
+#define NB_TRACE() do { if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64(); } while (0)
     for (uint32_t step = 0; step < g.n_steps; step++) {
+        if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64();
         const uint32_t pos = __ldcg(&g.st->pos);
+        const float pen = __ldcg(&g.st->penalty);
         const uint32_t range = __ldcg(&g.st->is_causal) ? pos + 1 : d.max_seq;
         uint32_t chunk = (range + g.nsplit_max - 1) / g.nsplit_max;
         chunk = max(chunk, 32u);
@@ -1329,9 +1347,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
         const uint32_t nsplit = (range + chunk - 1) / chunk;
 
         for (uint32_t l = 0; l < d.L; l++) {
-            const LayerW &lw = g.layers[l];
+            const LayerW &lw = lws[l];
             MatvecArgs a{};
-            a.d = d; a.st = g.st;
+            a.d = d; a.st = g.st; a.state_known = 1; a.pos_val = pos; a.pen_val = pen;
             // ---- P1: rmsnorm + quantise + QKV + V store ----
             a.w = lw.qkv_w; a.w_aux = lw.qkv_aux; a.rows = d.q_dim + 2 * d.kv_dim; a.n = d.E;
             a.src = g.x; a.gain = lw.g_attn; a.out = g.q; a.out_k = g.kraw; a.out_v = lw.vc;
@@ -1346,7 +1364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
                 const uint32_t bytes = (t1 - t0) * d.hd * 4u;
                 for (uint32_t off = threadIdx.x * 128u; off < bytes; off += kThreads * 128u) { prefetch_l2(kb + off); prefetch_l2(vb + off); }
             }
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P2: attention over (kv head, split) items ----
             {
                 AttnArgs t{};
@@ -1360,43 +1378,44 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
                 }
             }
             pf(lw.w13_w, lw.w13_aux, 2 * d.F, d.E, lw.g_ffn);
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P3: quantise(xba) + O + residual ----
             a.w = lw.wo_w; a.w_aux = lw.wo_aux; a.rows = d.E; a.n = d.q_dim;
             a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr;
             matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
             pf(lw.w2_w, lw.w2_aux, d.E, d.F, nullptr);
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P4: rmsnorm + quantise + W1|W3 + SwiGLU ----
             a.w = lw.w13_w; a.w_aux = lw.w13_aux; a.rows = 2 * d.F; a.n = d.E;
             a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb;
             matvec_phase<QUANT, EPI_SWIGLU, RBL, LPG>(a, cta, ncta, dsm, ms);
-            if (l + 1 < d.L) pf(g.layers[l + 1].qkv_w, g.layers[l + 1].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[l + 1].g_attn);
+            if (l + 1 < d.L) pf(lws[l + 1].qkv_w, lws[l + 1].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[l + 1].g_attn);
             else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 4, nullptr, 0, g.g_final);
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P5: quantise(hb) + W2 + residual ----
             a.w = lw.w2_w; a.w_aux = lw.w2_aux; a.rows = d.E; a.n = d.F;
             a.src = g.hb; a.gain = nullptr; a.out = g.x;
             matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
         }
         // ---- classifier: final rmsnorm + quantise + matvec + penalty + per-CTA argmax ----
         {
             MatvecArgs a{};
-            a.d = d; a.st = g.st; a.st_rw = g.st;
+            a.d = d; a.st = g.st; a.st_rw = g.st; a.state_known = 1; a.pos_val = pos; a.pen_val = pen;
             a.w = g.cls_w; a.w_aux = g.cls_aux; a.rows = d.V; a.n = d.E;
             a.src = g.x; a.gain = g.g_final; a.out = g.logits;
             a.seen = g.seen; a.seen_rw = g.seen; a.cls_val = g.cls_val; a.cls_idx = g.cls_idx; a.ids = g.ids;
             matvec_phase<QUANT, EPI_CLS, RBC, LPG>(a, cta, ncta, dsm, ms);
-            pf(g.layers[0].qkv_w, g.layers[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, g.layers[0].g_attn);
-            grid_barrier(g.bar, target, ncta);
+            pf(lws[0].qkv_w, lws[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[0].g_attn);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
             if (cta == 0) {
                 const uint32_t nxt = cls_finalize(a, ncta, ms);
                 if (step + 1 < g.n_steps) embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, nxt, d);
             }
-            grid_barrier(g.bar, target, ncta);
+            grid_barrier(g.bar, target, ncta); NB_TRACE();
         }
     }
+#undef NB_TRACE
 }
 
 }  // namespace nb
