@@ -463,6 +463,10 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     if (nb200_device_count() <= 0) return fail(NB200_ENODEV, "no CUDA device: nano_b200 has no CPU path");
     if (rd_u32(img) != 0x42443453u || rd_u32(img + 4) != 0x55524c4du) return fail(NB200_EINVAL, "bad magic (not a BD4SURLM file)");
     CK(cudaSetDevice(device));
+    {   // hosts that reach the engine through the reference API (infer.h has no flags argument) use the environment
+        const char *ex = getenv("NB200_EXACT");
+        if (ex && atoi(ex) != 0) flags |= NB200_FLAG_EXACT;
+    }
     nb200_engine *e = new nb200_engine();
     struct Guard { nb200_engine *e; bool ok = false; ~Guard() { if (!ok) nb200_engine_destroy(e); } } guard{e};
     e->device = device; e->flags = flags;
