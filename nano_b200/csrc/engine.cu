@@ -889,8 +889,8 @@ int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned lo
     if (!e || !stamps || !count) return fail(NB200_EINVAL, "null argument");
     if (!e->use_mega) return fail(NB200_EINVAL, "persistent kernel not active");
     CK(cudaSetDevice(e->device));
-    const uint32_t n = 5 * e->d.L + 4;
-    if (cap < n) return fail(NB200_EINVAL, "need room for %u stamps", n);
+    const uint32_t n = 1024 + 64;          // [0, 5L+4): per-barrier stamps; [1024, 1024+48): intra-phase stamps of layer L/2
+    if (cap < n || 5 * e->d.L + 4 > 1024) return fail(NB200_EINVAL, "need room for %u stamps", n);
     unsigned long long *buf = nullptr;
     CK(cudaMalloc(&buf, (size_t)n * 8));
     CK(cudaMemset(buf, 0, (size_t)n * 8));

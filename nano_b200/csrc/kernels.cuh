@@ -19,6 +19,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "expf_ref.cuh"
 
 namespace nb {
@@ -73,8 +75,10 @@ struct MatvecArgs {
     int8_t *dump_codes; float *dump_scales;
     // persistent kernel: step state already in registers (saves an L2 round trip per phase)
     uint32_t state_known, pos_val; float pen_val;
+    unsigned long long *dbg;     // optional: CTA 0 / thread 0 clock64() stamps inside the phase (tools/gpu_trace.py)
     Dims d;
 };
+#define NB_STAMP(ptr, k) do { if ((ptr) && blockIdx.x == 0 && threadIdx.x == 0) (ptr)[k] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -200,12 +204,15 @@ __device__ void prep_f32(const float *src, const float *__restrict__ gain, int n
 // tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
 template <int NT>
 __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n, int gs, bool exact,
-                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales) {
+                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales,
+                         unsigned long long *dbg = nullptr) {
     int8_t *codes = reinterpret_cast<int8_t *>(act);
     float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
     stage_vector<NT>(src, gain, n, stage);
+    NB_STAMP(dbg, 2);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
+    NB_STAMP(dbg, 3);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = n / gs, epl = gs / 32;      // elements per lane (gs in {32,64,128,256})
     for (int g = warp; g < G; g += NT / 32) {
@@ -530,6 +537,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     const uint32_t gwarp = cta * kWarps + warp, nwarps = ncta * kWarps;
     float *stage = reinterpret_cast<float *>(act + act_region_bytes(QUANT, a.n, (QUANT == 0x80) ? LPG * 16 : 1));
 
+    NB_STAMP(a.dbg, 0);
     // request this warp's first weight tile (and the residual it will add to) before the activation prologue
     Q80Tile<RB> pre;
     float xres[RB];
@@ -542,20 +550,33 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     }
 
     if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red);
-    else if (QUANT == 0x80) prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
+    else if (QUANT == 0x80) { NB_STAMP(a.dbg, 1); prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, a.dbg); }
     else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
 
+    NB_STAMP(a.dbg, 4);
     const uint32_t pos = a.state_known ? a.pos_val : (a.st ? __ldcg(&a.st->pos) : 0);
     float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
     float pen = 1.0f;
     if (EPI == EPI_CLS) pen = a.state_known ? a.pen_val : __ldcg(&a.st->penalty);
 
-    for (uint32_t rb = gwarp; rb < nblocks; rb += nwarps) {
+    // One row block = dot products + epilogue.  `first` is a compile-time tag: the first block of a warp consumes the
+    // tile (and residual) requested before the prologue straight from registers.  (A run-time `&pre : nullptr` select
+    // forces the tile through local memory, and local memory misses to L2 after every barrier's L1 invalidation.)
+    auto do_block = [&](const uint32_t rb, auto first_tag) {
+        constexpr bool kFirst = decltype(first_tag)::value;
         const uint32_t row0 = rb * RB;
         float val[RB];
         if (QUANT == 0x00) rows_f32<RB>(static_cast<const float *>(a.w), row0, a.rows, a.n, act, val);
-        else if (QUANT == 0x80) rows_q80<RB, LPG>(static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, act, val, rb == gwarp ? &pre : nullptr);
-        else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
+        else if (QUANT == 0x80) {
+#pragma unroll
+            for (int r = 0; r < RB; r++) val[r] = 0.0f;
+            if (kFirst) q80_consume<RB, LPG>(pre, a.n, 0, act, val);
+            for (uint32_t k0 = kFirst ? 1024u : 0u; k0 < a.n; k0 += 1024) {
+                Q80Tile<RB> t;
+                q80_load<RB, LPG>(t, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, k0);
+                q80_consume<RB, LPG>(t, a.n, k0, act, val);
+            }
+        } else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
 
         if (EPI == EPI_SWIGLU) {
             // rows (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
@@ -575,7 +596,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 if (row >= a.rows) break;
                 float v = val[r];
                 if (EPI == EPI_STORE) { if (lane == 0) a.out[row] = v; }
-                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(rb == gwarp ? xres[r] : __ldcg(a.out + row), v); }
+                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(kFirst ? xres[r] : __ldcg(a.out + row), v); }
                 else if (EPI == EPI_QKV) {
                     if (lane == 0) {
                         if (row < d.q_dim) a.out[row] = v;
@@ -593,8 +614,13 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 }
             }
         }
+    };
+    if (has_first) {
+        if (QUANT == 0x80) do_block(gwarp, std::true_type{}); else do_block(gwarp, std::false_type{});
+        for (uint32_t rb = gwarp + nwarps; rb < nblocks; rb += nwarps) do_block(rb, std::false_type{});
     }
 
+    NB_STAMP(a.dbg, 5);
     if (EPI == EPI_CLS) {
         // rows were visited in ascending order per warp, so (bestv,besti) already holds the warp's first max
         if (lane == 0) { ms.best_v[warp] = bestv; ms.best_i[warp] = besti; }
@@ -1265,10 +1291,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
 }
 
 // Monotonic counter barrier across the persistent grid (all CTAs co-resident: cooperative launch).
-__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &target, uint32_t ncta) {
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, volatile unsigned int &target_smem, uint32_t ncta) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += ncta;
+        const unsigned int target = target_smem + ncta;      // lives in shared memory: every poll invalidates L1, so a
+        target_smem = target;                                // spilled register would cost an L2 round trip per barrier
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");   // release: this CTA's phase outputs
         while (ld_acquire_u32(ctr) < target) { }
     }
@@ -1306,10 +1333,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ MatvecSmem ms;
     __shared__ uint32_t attn_flag;
-    constexpr int RBL = 2, RBC = 4;                 // rows per warp task: layer matrices / classifier
+    __shared__ unsigned int target;
+    __shared__ uint32_t ti;
+    constexpr int RBL = 2, RBC = 2;                 // rows per warp task: layer matrices / classifier
     const uint32_t cta = blockIdx.x, ncta = gridDim.x;
     const Dims &d = g.d;
-    unsigned int target = 0;
+    if (threadIdx.x == 0) { target = 0; ti = 0; }
 
     // The per-layer pointer table lives in shared memory: every grid barrier invalidates L1 (CCTL.IVALL), so a
     // table left in HBM costs a chain of dependent L2 round trips at the start of every phase.
@@ -1334,7 +1363,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
     pf(lws[0].qkv_w, lws[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[0].g_attn);
     grid_barrier(g.bar, target, ncta);
 
-    uint32_t ti = 0;
 #define NB_TRACE() do { if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64(); } while (0)
     for (uint32_t step = 0; step < g.n_steps; step++) {
         if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64();
@@ -1350,11 +1378,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
             const LayerW &lw = lws[l];
             MatvecArgs a{};
             a.d = d; a.st = g.st; a.state_known = 1; a.pos_val = pos; a.pen_val = pen;
+            unsigned long long *dbg = (g.trace && l == d.L / 2 && step + 1 == g.n_steps) ? g.trace + 1024 : nullptr;
+            a.dbg = dbg;
             // ---- P1: rmsnorm + quantise + QKV + V store ----
             a.w = lw.qkv_w; a.w_aux = lw.qkv_aux; a.rows = d.q_dim + 2 * d.kv_dim; a.n = d.E;
             a.src = g.x; a.gain = lw.g_attn; a.out = g.q; a.out_k = g.kraw; a.out_v = lw.vc;
             a.dump_codes = g.dump_codes; a.dump_scales = g.dump_scales;
             matvec_phase<QUANT, EPI_QKV, RBL, LPG>(a, cta, ncta, dsm, ms);
+            NB_STAMP(dbg, 6);
             pf(lw.wo_w, lw.wo_aux, d.E, d.q_dim, nullptr);
             if (cta < d.KV * nsplit) {          // the K/V chunk of this CTA's attention item (old rows: already final)
                 const uint32_t ag = cta / nsplit, as = cta % nsplit;
@@ -1381,14 +1412,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
             grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P3: quantise(xba) + O + residual ----
             a.w = lw.wo_w; a.w_aux = lw.wo_aux; a.rows = d.E; a.n = d.q_dim;
-            a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr;
+            a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr; a.dbg = dbg ? dbg + 16 : nullptr;
             matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
+            NB_STAMP(dbg, 16 + 6);
             pf(lw.w2_w, lw.w2_aux, d.E, d.F, nullptr);
             grid_barrier(g.bar, target, ncta); NB_TRACE();
             // ---- P4: rmsnorm + quantise + W1|W3 + SwiGLU ----
             a.w = lw.w13_w; a.w_aux = lw.w13_aux; a.rows = 2 * d.F; a.n = d.E;
-            a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb;
+            a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb; a.dbg = dbg ? dbg + 32 : nullptr;
             matvec_phase<QUANT, EPI_SWIGLU, RBL, LPG>(a, cta, ncta, dsm, ms);
+            NB_STAMP(dbg, 32 + 6);
             if (l + 1 < d.L) pf(lws[l + 1].qkv_w, lws[l + 1].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[l + 1].g_attn);
             else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 4, nullptr, 0, g.g_final);
             grid_barrier(g.bar, target, ncta); NB_TRACE();

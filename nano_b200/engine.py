@@ -169,7 +169,7 @@ class Engine:
 
     def trace_token(self, token: int, pos: int) -> np.ndarray:
         """clock64() stamps (SM cycles) of CTA 0 after every grid barrier of one token (persistent kernel only)."""
-        cap = 5 * self.n_layer + 8
+        cap = 1024 + 64
         buf = np.zeros(cap, np.uint64); n = C.c_uint32(0)
         _check(lib().nb200_trace_token(self.h, token, pos, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return buf[: n.value]
