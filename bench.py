@@ -333,9 +333,14 @@ def main():
             per_class[name] = {"launches": int(cnt[i]), "mean_us": dur * 1e6, "share": float(ms[i]) / tot_ms,
                                "alg_bytes": alg[name], "gbs": alg[name] / dur / 1e9}
     dom = "w13_swiglu"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": f"k_matvec<{'Q80' if quant == mf.QUANT_Q80 else 'Q4K' if quant == mf.QUANT_Q4K else 'F32'},SWIGLU> (W1|W3 + SwiGLU)",
             "achieved": per_class[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": per_class[dom]["gbs"] / peak,
-            "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": alg[dom],
+            "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/r1_ncu_full_multikernel.md" if traffic else None, "peak_source": peak_src, "alg_bytes_per_launch": alg[dom],
             "mean_launch_us": per_class[dom]["mean_us"], "share_of_step": per_class[dom]["share"],
             "per_kernel": per_class}
     avg_pos = (PROMPT + seq - 1) / 2.0

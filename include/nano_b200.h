@@ -43,6 +43,7 @@ extern "C" {
 #define NB200_FLAG_NO_GRAPH 0x2u   /* launch kernels directly instead of replaying a CUDA graph */
 #define NB200_FLAG_NO_PDL 0x4u     /* disable programmatic dependent launch */
 #define NB200_FLAG_NO_MEGA 0x8u    /* use the multi-kernel path instead of the persistent megakernel */
+#define NB200_FLAG_NO_CLUSTER 0x10u /* do not use the cluster-resident kernel (16-CTA cluster, DSMEM activations) */
 
 /* quantisation / architecture ids: identical to infer/tensor.h:72-76 and infer/infer.h:45-47 */
 #define NB200_QUANT_F32 0x00u

@@ -27,6 +27,7 @@
 
 #include "../../include/nano_b200.h"
 #include "kernels.cuh"
+#include "cluster.cuh"
 
 using namespace nb;
 
@@ -100,6 +101,8 @@ struct nb200_engine {
     bool use_pdl = true;
     // persistent megakernel (fast mode): one cooperative launch runs n tokens
     unsigned long long *trace_dev = nullptr;
+    // cluster-resident path (cluster.cuh)
+    bool use_cluster = false; const void *cl_kern = nullptr; ClusterArgs cl{}; uint32_t cl_smem = 0;
     bool use_mega = false; const void *mega_kern = nullptr; uint32_t mega_smem = 0, mega_phase_smem = 0; LayerW *layers_dev = nullptr; unsigned int *bar = nullptr;
     uint64_t launches = 0, weight_bytes = 0;
     uint32_t launches_per_token = 0;
@@ -357,7 +360,25 @@ int launch_mega(nb200_engine *e, uint32_t n_steps) {
     return 0;
 }
 
+// n_steps tokens in one launch of the 16-CTA cluster kernel
+int launch_cluster(nb200_engine *e, uint32_t n_steps) {
+    if (n_steps == 0) return 0;
+    ClusterArgs g = e->cl;
+    g.n_steps = n_steps;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = e->cl_smem; cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    void *params[] = {&g};
+    CK(cudaLaunchKernelExC(&cfg, e->cl_kern, params));
+    e->launches++;
+    return 0;
+}
+
 int launch_token(nb200_engine *e) {
+    if (e->use_cluster) return launch_cluster(e, 1);
     if (e->use_mega) return launch_mega(e, 1);
     if (e->graph) {
         CK(cudaGraphLaunch(e->graph, e->stream));
@@ -427,6 +448,152 @@ int put_rows(nb200_engine *e, Mat &m, const uint8_t *w, const uint8_t *aux, uint
         CK(cudaDeviceSynchronize());
         return 0;
     }
+}
+
+// ---------------- cluster-resident path: weight stream + schedule ----------------
+// copy one fused Q80 matrix into the per-rank tile stream: tile = [rows x n codes][rows x G scales]
+__global__ void k_build_stream(const uint8_t *__restrict__ codes, const float *__restrict__ scales, uint32_t rows_per_rank, uint32_t n, uint32_t G,
+                               uint32_t T, uint32_t tile_stride, uint8_t *stream, uint64_t rank_stride, uint64_t phase_off) {
+    const uint32_t rank = blockIdx.y;
+    const uint32_t chunks_per_row = n / 16 + (G * 4 + 15) / 16;       // 16-byte chunks of codes, then of scales (scales copied per float below)
+    (void)chunks_per_row;
+    for (uint32_t lrow = blockIdx.x; lrow < rows_per_rank; lrow += gridDim.x) {
+        const uint32_t j = lrow / T, i = lrow % T;
+        const uint32_t rows = min(T, rows_per_rank - j * T);
+        uint8_t *tile = stream + (uint64_t)rank * rank_stride + phase_off + (uint64_t)j * tile_stride;
+        const uint64_t grow = (uint64_t)rank * rows_per_rank + lrow;
+        const int4 *src = reinterpret_cast<const int4 *>(codes + grow * n);
+        int4 *dst = reinterpret_cast<int4 *>(tile + (uint64_t)i * n);
+        for (uint32_t c = threadIdx.x; c < n / 16; c += blockDim.x) dst[c] = src[c];
+        float *sdst = reinterpret_cast<float *>(tile + (uint64_t)rows * n) + (uint64_t)i * G;
+        for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) sdst[c] = scales[grow * G + c];
+    }
+}
+
+typedef void (*ClusterKern)(const ClusterArgs);
+template <int LPG>
+ClusterKern pick_cluster_kvm(uint32_t kvm) {
+    switch (kvm) {
+        case 1: return k_decode_cluster<LPG, 1>;
+        case 2: return k_decode_cluster<LPG, 2>;
+        case 4: return k_decode_cluster<LPG, 4>;
+        default: return nullptr;
+    }
+}
+
+// returns 0 and sets e->use_cluster when the model fits the cluster-resident kernel; 0 without setting it otherwise
+int setup_cluster(nb200_engine *e) {
+    const Dims &d = e->d;
+    if (d.quant != 0x80u || d.exact || d.hd > 128 || (d.gs != 64 && d.gs != 128) || d.KV > (uint32_t)kCluster || kCluster % d.KV) return 0;
+    ClusterKern k = (d.gs == 128) ? pick_cluster_kvm<8>(d.kv_mul) : pick_cluster_kvm<4>(d.kv_mul);
+    if (!k) return 0;
+    const uint32_t L = d.L, E = d.E, QD = d.q_dim, KD = d.kv_dim, F = d.F, V = d.V;
+    struct PM { const Mat *m; uint32_t epi, has_gain, src_sel, layer; };
+    std::vector<PM> pms;
+    for (uint32_t l = 0; l < L; l++) {
+        pms.push_back({&e->qkv[l], (uint32_t)EPI_QKV, 1u, 0u, l});
+        pms.push_back({&e->wo[l], (uint32_t)EPI_RESID, 0u, 1u, l});
+        pms.push_back({&e->w13[l], (uint32_t)EPI_SWIGLU, 1u, 0u, l});
+        pms.push_back({&e->w2[l], (uint32_t)EPI_RESID, 0u, 2u, l});
+    }
+    pms.push_back({&e->cls, (uint32_t)EPI_CLS, 1u, 0u, L});
+    for (auto &pm : pms) if (pm.m->rows % (2 * kCluster) || pm.m->n % 16) return 0;
+    (void)QD; (void)KD; (void)F; (void)V;
+
+    // stage size and per-phase tile geometry
+    const uint32_t stage_cap = 34 * 1024;
+    uint32_t stage_bytes = (E * 4 + 127) & ~127u;
+    std::vector<ClPhase> ph(pms.size());
+    uint64_t off = 0; uint32_t tile_idx = 0;
+    for (size_t i = 0; i < pms.size(); i++) {
+        const Mat &m = *pms[i].m;
+        const uint32_t G = m.n / d.gs, rpr = m.rows / kCluster, rowb = m.n + 4 * G;
+        uint32_t T = stage_cap / rowb; T &= ~1u; if (T > 32) T = 32; if (T > rpr) T = rpr; if (T < 2) return 0;
+        const uint32_t tstride = (T * rowb + 15u) & ~15u;
+        if (tstride > stage_bytes) stage_bytes = (tstride + 127u) & ~127u;
+        ClPhase &c = ph[i];
+        memset(&c, 0, sizeof c);
+        c.stream_off = off; c.has_gain = pms[i].has_gain; c.rows_per_rank = rpr; c.rows_per_tile = T; c.tile_stride = tstride;
+        c.n = m.n; c.epi = pms[i].epi; c.layer = pms[i].layer; c.pad = pms[i].src_sel;
+        c.ntiles = (rpr + T - 1) / T;
+        c.tile_base = tile_idx; tile_idx += c.ntiles + (c.has_gain ? 1u : 0u);
+        c.gain_off = (pms[i].epi == EPI_QKV) ? (uint64_t)pms[i].layer * E * 4
+                   : (pms[i].epi == EPI_SWIGLU) ? ((uint64_t)L + pms[i].layer) * E * 4 : (uint64_t)2 * L * E * 4;
+        off += (uint64_t)c.ntiles * tstride;
+        off = (off + 127u) & ~(uint64_t)127u;
+    }
+    const uint64_t rank_stride = off;
+
+    // shared-memory plan
+    auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
+    const uint32_t rpk = kCluster / d.KV;
+    uint32_t lpr = 1; while (lpr * 4 < d.hd) lpr <<= 1;
+    const uint32_t rpw = 32 / lpr;
+    uint32_t capmax = (d.max_seq + rpk - 1) / rpk; capmax = (capmax + 7u) & ~7u; capmax = (capmax + 7u) & ~7u;
+    const uint32_t attn_floats = d.kv_mul * d.hd + d.hd + ((2 * d.kv_mul + 3) & ~3u) + d.kv_mul * capmax + kWarps * rpw * d.kv_mul * d.hd + 16;
+    uint32_t maxn = E; if (d.q_dim > maxn) maxn = d.q_dim; if (d.F > maxn) maxn = d.F;
+    uint32_t o = 0;
+    ClusterArgs &g = e->cl;
+    memset(&g, 0, sizeof g);
+    g.off_phases = o; o += al((uint32_t)(ph.size() * sizeof(ClPhase)));
+    g.off_x = o; o += al(E * 4); g.off_q = o; o += al(d.q_dim * 4); g.off_kraw = o; o += al(d.kv_dim * 4); g.off_vrow = o; o += al(d.kv_dim * 4);
+    g.off_xba = o; o += al(d.q_dim * 4); g.off_hb = o; o += al(d.F * 4);
+    g.off_part = o; o += al(d.KV * rpk * d.kv_mul * (d.hd + 2) * 4);
+    g.off_act = o; o += al(act_region_bytes(0x80u, maxn, d.gs));
+    g.off_slots = o; o += al(2 * kCluster * 4);
+    g.off_attn = o; o += al(attn_floats * 4);
+    g.off_ring = o;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+    const uint32_t static_smem = 2048;
+    if ((uint32_t)max_optin < o + static_smem + 2 * stage_bytes) return 0;
+    uint32_t nst = ((uint32_t)max_optin - static_smem - o) / stage_bytes;
+    if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
+    if (nst < 2) return 0;
+    const uint32_t smem = o + nst * stage_bytes;
+
+    cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (ce != cudaSuccess) { cudaGetLastError(); return 0; }
+    {   // can one 16-CTA cluster be resident?
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int ncl = 0;
+        ce = cudaOccupancyMaxActiveClusters(&ncl, (const void *)k, &cfg);
+        if (ce != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
+    }
+
+    // device objects: stream, shared gains, phase table
+    uint8_t *stream = nullptr; float *gains = nullptr; ClPhase *phd = nullptr;
+    DM(stream, rank_stride * kCluster + 256);
+    DM(gains, ((size_t)2 * L + 1) * E * 4 + 256);
+    DM(phd, ph.size() * sizeof(ClPhase));
+    CK(cudaMemcpy(gains, e->norm_attn, (size_t)L * E * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(gains + (size_t)L * E, e->norm_ffn, (size_t)L * E * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(gains + (size_t)2 * L * E, e->norm_final, (size_t)E * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(phd, ph.data(), ph.size() * sizeof(ClPhase), cudaMemcpyHostToDevice));
+    CK(cudaMemset(stream, 0, rank_stride * kCluster + 256));
+    for (size_t i = 0; i < pms.size(); i++) {
+        const Mat &m = *pms[i].m;
+        const ClPhase &c = ph[i];
+        uint32_t gx = c.rows_per_rank < 1024 ? c.rows_per_rank : 1024;
+        k_build_stream<<<dim3(gx, kCluster), 128>>>((const uint8_t *)m.w, (const float *)m.aux, c.rows_per_rank, m.n, m.n / d.gs, c.rows_per_tile,
+                                                  c.tile_stride, stream, rank_stride, c.stream_off);
+        CK(cudaGetLastError());
+    }
+    CK(cudaDeviceSynchronize());
+    e->weight_bytes += rank_stride * kCluster;
+
+    g.stream = stream; g.rank_stride = rank_stride; g.shared_base = (const uint8_t *)gains; g.phases = phd;
+    g.nphases = (uint32_t)ph.size(); g.tiles_per_token = tile_idx; g.nstages = nst; g.stage_bytes = stage_bytes;
+    g.emb_w = e->emb.w; g.emb_aux = e->emb.aux; g.logits = e->logits; g.kc = e->kc; g.vc = e->vc;
+    g.qnorm = e->qnorm; g.knorm = e->knorm; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
+    g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.n_steps = 1; g.d = d;
+    e->cl_kern = (const void *)k; e->cl_smem = smem; e->use_cluster = true; e->launches_per_token = 1;
+    return 0;
 }
 
 }  // namespace
@@ -688,8 +855,12 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
             cudaGetLastError();
         }
     }
-    if (e->use_mega) {
-        // nothing to capture: a token (or a whole run of tokens) is one cooperative launch
+    {
+        const char *cl_env = getenv("NB200_CLUSTER");
+        if (!(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0)) { if ((r = setup_cluster(e))) return r; }
+    }
+    if (e->use_mega || e->use_cluster) {
+        // nothing to capture: a token (or a whole run of tokens) is one launch
     } else if (!(flags & NB200_FLAG_NO_GRAPH)) {
         r = capture_graph(e);
         if (r && e->use_pdl) {          // retry without PDL edges before giving up on the graph
@@ -792,10 +963,12 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
     e->seen_valid = false; e->seen_mirror.clear();
     CK(cudaEventRecord(ev[0], e->stream));
-    if (e->use_mega) { if ((r = launch_mega(e, n_prompt - 1))) return r; }
+    if (e->use_cluster) { if ((r = launch_cluster(e, n_prompt - 1))) return r; }
+    else if (e->use_mega) { if ((r = launch_mega(e, n_prompt - 1))) return r; }
     else for (uint32_t p = 0; p + 1 < n_prompt; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[1], e->stream));
-    if (e->use_mega) { if ((r = launch_mega(e, n_total - n_prompt))) return r; }
+    if (e->use_cluster) { if ((r = launch_cluster(e, n_total - n_prompt))) return r; }
+    else if (e->use_mega) { if ((r = launch_mega(e, n_total - n_prompt))) return r; }
     else for (uint32_t p = n_prompt - 1; p + 1 < n_total; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[2], e->stream));
     CK(cudaMemcpyAsync(ids, e->ids_dev, (size_t)n_total * 4, cudaMemcpyDeviceToHost, e->stream));

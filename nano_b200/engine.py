@@ -18,7 +18,7 @@ u32p = C.POINTER(C.c_uint32)
 u8p = C.POINTER(C.c_uint8)
 i8p = C.POINTER(C.c_int8)
 
-FLAG_EXACT, FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGA = 0x1, 0x2, 0x4, 0x8
+FLAG_EXACT, FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGA, FLAG_NO_CLUSTER = 0x1, 0x2, 0x4, 0x8, 0x10
 F_X, F_XBA, F_HB, F_Q, F_LOGITS, F_KROW, F_VROW, F_ACT_I8, F_ACT_SCALE = 0, 2, 4, 6, 9, 13, 14, 20, 21
 
 EXPORTS = [

@@ -64,7 +64,7 @@ def reference_noise_floor(name, quant, gs, path, S):
     return floor
 
 
-@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_MEGA], ids=["megakernel", "multikernel"])
+@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_CLUSTER, E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA], ids=["cluster", "megakernel", "multikernel"])
 @pytest.mark.parametrize("name,quant,gs", TOY)
 def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags):
     """Fast mode (parallel fp32 reductions): within the north-star tolerance, or -- where the reference's own
@@ -168,7 +168,7 @@ def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty):
         eng.close()
     # fast mode: device loop == API loop, and persistent megakernel == multi-kernel graph (same phase code)
     runs = []
-    for flags in (0, E.FLAG_NO_MEGA):
+    for flags in (E.FLAG_NO_CLUSTER, E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA):
         eng = E.Engine(path, S, flags=flags)
         a = np.zeros(S + 1, np.uint32); a[:P] = prompt
         for pos in range(S - 1):
@@ -180,6 +180,20 @@ def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty):
         eng.close()
     assert runs[0][0] == runs[1][0]
     assert_bits_equal(runs[0][1], runs[1][1], "megakernel vs multi-kernel logits")
+    # cluster-resident kernel (default path when the model fits): API loop == device loop; ids equal to the other
+    # paths whenever every step's top-1/top-2 margin is comfortably above fast-mode noise
+    eng = E.Engine(path, S)
+    a = np.zeros(S + 1, np.uint32); a[:P] = prompt
+    margins = []
+    for pos in range(S - 1):
+        a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
+        lg = np.sort(eng.logits()); margins.append(float(lg[-1] - lg[-2]))
+    b = np.zeros(S + 1, np.uint32); b[:P] = prompt
+    eng.decode_greedy(b, P, S, penalty)
+    assert a[:S].tolist() == b[:S].tolist()
+    if min(margins[P - 1:]) > 1e-3:
+        assert a[:S].tolist() == runs[0][0]
+    eng.close()
     o.close()
 
 

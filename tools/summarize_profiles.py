@@ -1,0 +1,47 @@
+"""Turn ncu artefacts (gpurun_out/) into the small tracked summaries under profiles/."""
+import collections, csv, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+def launch_list(path, out_md, title):
+    lines = [l for l in open(path) if l.startswith('"')]
+    agg = collections.OrderedDict()
+    tot = 0.0
+    for row in csv.DictReader(lines):
+        try: v = float(row["Metric Value"].replace(",", ""))
+        except Exception: continue
+        unit = row["Metric Unit"]
+        us = v / 1000.0 if unit in ("ns", "nsecond") else v * (1000.0 if unit in ("ms", "msecond") else 1.0)
+        key = (row["Kernel Name"], row["Grid Size"], row["Block Size"])
+        agg.setdefault(key, []).append(us); tot += us
+    with open(out_md, "w") as f:
+        f.write(f"# {title}\n\nSource: `{os.path.relpath(path, ROOT)}` (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
+        f.write("| kernel | grid | block | launches | mean us | share of listed time |\n|---|---|---|---|---|---|\n")
+        for (k, g, b), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"| `{k[:90]}` | {g} | {b} | {len(v)} | {sum(v)/len(v):.2f} | {100*sum(v)/tot:.1f}% |\n")
+
+def full_report(rep, out_md, title):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
+    hdr, units = r[0], r[1]
+    want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
+    idx = [hdr.index(w) for w in want if w in hdr]
+    with open(out_md, "w") as f:
+        f.write(f"# {title}\n\nSource: `{os.path.relpath(rep, ROOT)}` (`ncu --set full --clock-control none --import-source on`), one row per captured launch.\n\n")
+        f.write("| " + " | ".join(f"{hdr[i]} ({units[i]})" if units[i] else hdr[i] for i in idx) + " |\n|" + "---|" * len(idx) + "\n")
+        for row in r[2:]:
+            f.write("| " + " | ".join(row[i][:70] for i in idx) + " |\n")
+
+if __name__ == "__main__":
+    g = os.path.join(ROOT, "gpurun_out"); p = os.path.join(ROOT, "profiles")
+    os.makedirs(p, exist_ok=True)
+    for src, dst, title in [("r1/launches_multikernel.csv", "r1_launches_multikernel.md", "Round 1 - launch list, multi-kernel graph path, Nano-168M Q80 seq 512"),
+                            ("launches_r1.csv", "r1_launches_first_version.md", "Round 1 - launch list of the first working version (before fusion fixes)")]:
+        if os.path.exists(os.path.join(g, src)): launch_list(os.path.join(g, src), os.path.join(p, dst), title)
+    for src, dst, title in [("r1/prof_multikernel.ncu-rep", "r1_ncu_full_multikernel.md", "Round 1 - ncu --set full, multi-kernel path kernels (Nano-168M Q80)"),
+                            ("prof_mega_v1.ncu-rep", "r1_ncu_full_megakernel.md", "Round 1 - ncu --set full, persistent megakernel k_decode_mega (one launch = 496 tokens, under profiler)")]:
+        if os.path.exists(os.path.join(g, src)): full_report(os.path.join(g, src), os.path.join(p, dst), title)
+    for b in os.listdir(os.path.join(g, "r1")) if os.path.isdir(os.path.join(g, "r1")) else []:
+        if b.startswith("bench_") and b.endswith(".json"):
+            open(os.path.join(p, "r1_" + b), "w").write(open(os.path.join(g, "r1", b)).read())
