@@ -21,7 +21,7 @@
 namespace nb {
 
 constexpr int kCluster = 16;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 struct ClPhase {              // one matvec phase of the per-token schedule (identical for all ranks)
     uint64_t stream_off;      // byte offset of this phase's first weight tile inside a rank's stream
@@ -30,6 +30,9 @@ struct ClPhase {              // one matvec phase of the per-token schedule (ide
     uint32_t ntiles;          // weight tiles
     uint32_t has_gain;
     uint32_t rows_per_rank, rows_per_tile, tile_stride, n, epi, layer, pad;   // pad: source vector (0 x, 1 attention output, 2 SwiGLU output)
+    uint32_t row_stride;      // bytes between rows inside a tile: n + 16 (keeps lane-per-row 128-bit smem reads conflict-free)
+    uint32_t gs_stride;       // floats between the scale rows of a tile: (n/gs) | 1 (odd => conflict-free)
+    uint32_t pad2[2];
 };
 
 struct ClusterArgs {
@@ -42,8 +45,10 @@ struct ClusterArgs {
     const float *qnorm, *knorm, *rope_cos, *rope_sin;
     DevState *st; uint32_t *ids; uint8_t *seen;
     uint32_t n_steps;
+    unsigned long long *trace;          // optional: rank 0 / thread 0 clock64() stamps during the LAST step
     Dims d;
 };
+#define CL_STAMP() do { if (g.trace && rank == 0 && threadIdx.x == 0 && step + 1 == g.n_steps && ti < 1000) g.trace[ti++] = clock64(); } while (0)
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,42 +96,101 @@ __device__ __forceinline__ void scatter_u32(uint32_t *local_slot, uint32_t v) {
 
 // ---------------------------------------------------------------- weight ring
 struct Ring {
+    volatile uint32_t *tile_id;   // [nstages] global index of the tile currently assigned to the stage (written by the producer).
+                                  // mbarrier parity waits are only unambiguous one phase apart; tiles of one stage are consumed
+                                  // by DIFFERENT warps, and a fast warp can be several uses ahead -- it first waits for its tile
+                                  // to own the stage, then for the bytes.
     uint64_t *full, *empty;       // [nstages]
     unsigned char *buf;           // nstages * stage_bytes
     uint32_t nstages, stage_bytes;
 };
 
-// producer cursor (lives in the registers of warp 0 / lane 0)
+// consumer side: wait until tile `t` owns its stage and its bytes have landed (32-bit tile counters: a run is < 2^32 tiles)
+__device__ __forceinline__ uint32_t ring_wait_tile(const Ring &r, uint32_t t) {
+    const uint32_t use = t / r.nstages, s = t - use * r.nstages;
+    while (r.tile_id[s] != t) { }
+    mbar_wait(&r.full[s], use & 1u);
+    return s;
+}
+
+// producer cursor (lives in the registers of warp 0 / lane 0); everything incremental: no divisions on the issue path
 struct Producer {
-    uint64_t issued, total;       // global tile counters
-    uint32_t phase, j;            // next tile to issue: phase index within the token, tile index within the phase (-1 => header)
-    int32_t jj;
+    uint32_t issued, total;       // global tile counters
+    uint32_t s, par;              // stage and empty-barrier parity of the next tile to issue
+    uint32_t phase;               // phase (within the token) of the next tile to issue
+    int32_t jj;                   // its index within the phase (-1 => the header tile carrying the rmsnorm gain)
+    const uint8_t *src;           // its source address
+    uint32_t rows_left;           // rows of the phase not yet issued
 };
 
-// issue tiles until the ring is NST ahead of tile `t` (called by warp 0 / lane 0 only)
-__device__ __forceinline__ void ring_refill(const ClusterArgs &g, const ClPhase *ph, const Ring &r, Producer &p, uint64_t t, uint32_t rank) {
-    while (p.issued < p.total && p.issued < t + r.nstages) {
-        const uint32_t s = (uint32_t)(p.issued % r.nstages);
-        const uint32_t use = (uint32_t)(p.issued / r.nstages);
-        mbar_wait(&r.empty[s], (use & 1u) ^ 1u);                 // previous occupant fully consumed (passes at once on first use)
+__device__ __forceinline__ void producer_enter_phase(const ClusterArgs &g, const ClPhase *ph, Producer &p, uint32_t rank) {
+    const ClPhase &c = ph[p.phase];
+    p.jj = c.has_gain ? -1 : 0;
+    p.src = g.stream + (uint64_t)rank * g.rank_stride + c.stream_off;
+    p.rows_left = c.rows_per_rank;
+}
+
+// Issue ring tiles with global index < limit (warp 0 / lane 0 only).  blocking: wait until the stage's previous
+// occupant has been released; otherwise stop at the first busy stage (opportunistic prefetch of later phases).
+__device__ __forceinline__ void produce(const ClusterArgs &g, const ClPhase *ph, const Ring &r, Producer &p, uint32_t limit, bool blocking, uint32_t rank) {
+    if (limit > p.total) limit = p.total;
+    while (p.issued < limit) {
+        if (blocking) mbar_wait(&r.empty[p.s], p.par);
+        else if (!mbar_try_wait(&r.empty[p.s], p.par)) return;
         const ClPhase &c = ph[p.phase];
         const uint8_t *src; uint32_t bytes;
         if (p.jj < 0) {                                          // header tile: rmsnorm gain, shared by all ranks
             src = g.shared_base + c.gain_off; bytes = (c.n * 4u + 15u) & ~15u;
         } else {
-            const uint32_t rows = min(c.rows_per_tile, c.rows_per_rank - (uint32_t)p.jj * c.rows_per_tile);
-            const uint32_t G = c.n / g.d.gs;
-            src = g.stream + (uint64_t)rank * g.rank_stride + c.stream_off + (uint64_t)p.jj * c.tile_stride;
-            bytes = (rows * (c.n + 4u * G) + 15u) & ~15u;
+            const uint32_t rows = min(c.rows_per_tile, p.rows_left);
+            src = p.src; bytes = (rows * (c.row_stride + 4u * c.gs_stride) + 15u) & ~15u;
+            p.src += c.tile_stride; p.rows_left -= rows;
         }
-        mbar_expect_tx(&r.full[s], bytes);
-        bulk_g2s(r.buf + (size_t)s * r.stage_bytes, src, bytes, &r.full[s]);
+        r.tile_id[p.s] = p.issued;
+        mbar_expect_tx(&r.full[p.s], bytes);
+        bulk_g2s(r.buf + p.s * r.stage_bytes, src, bytes, &r.full[p.s]);
         p.issued++;
+        if (++p.s == r.nstages) { p.s = 0; p.par ^= 1u; }
         p.jj++;
-        if (p.jj >= (int32_t)c.ntiles) {                         // next phase (wrap to the next token)
-            p.phase++;
-            if (p.phase >= g.nphases) p.phase = 0;
-            p.jj = ph[p.phase].has_gain ? -1 : 0;
+        if (p.jj >= (int32_t)c.ntiles) {                         // next phase (wraps to the next token)
+            if (++p.phase >= g.nphases) p.phase = 0;
+            producer_enter_phase(g, ph, p, rank);
+        }
+    }
+}
+
+// One lane = one weight row resident in shared memory: no cross-lane reductions at all.  Integer group dots are exact;
+// the fp32 combine is the reference's left-to-right sum over groups (infer.c:668-674).
+template <int LPG>
+__device__ __forceinline__ float cl_row_dot(const unsigned char *wrow, const float *srow, uint32_t n, const unsigned char *act) {
+    constexpr uint32_t gs = LPG * 16;
+    const unsigned char *codes = act;
+    const float *xs = reinterpret_cast<const float *>(act + ((n + 15) & ~15));
+    const uint32_t G = n / gs;
+    float val = 0.0f;
+    for (uint32_t gi = 0; gi < G; gi++) {
+        int i0 = 0, i1 = 0;
+#pragma unroll
+        for (int ch = 0; ch < LPG; ch += 2) {
+            const int4 w0 = *reinterpret_cast<const int4 *>(wrow + gi * gs + ch * 16), x0 = *reinterpret_cast<const int4 *>(codes + gi * gs + ch * 16);
+            const int4 w1 = *reinterpret_cast<const int4 *>(wrow + gi * gs + ch * 16 + 16), x1 = *reinterpret_cast<const int4 *>(codes + gi * gs + ch * 16 + 16);
+            i0 = __dp4a(w0.x, x0.x, i0); i0 = __dp4a(w0.y, x0.y, i0); i0 = __dp4a(w0.z, x0.z, i0); i0 = __dp4a(w0.w, x0.w, i0);
+            i1 = __dp4a(w1.x, x1.x, i1); i1 = __dp4a(w1.y, x1.y, i1); i1 = __dp4a(w1.z, x1.z, i1); i1 = __dp4a(w1.w, x1.w, i1);
+        }
+        val = __fadd_rn(val, __fmul_rn(__fmul_rn((float)(i0 + i1), srow[gi]), xs[gi]));
+    }
+    return val;
+}
+
+// every lane writes its own value into the same slot of all 16 replicas
+__device__ __forceinline__ void scatter_lane_f32(float *local_slot, float v, bool active) {
+    const uint32_t a = smem_u32(local_slot);
+#pragma unroll
+    for (int r = 0; r < kCluster; r++) {
+        if (active) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(a), "r"(r));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
         }
     }
 }
@@ -162,9 +226,10 @@ __device__ __forceinline__ void cl_prep_q80(const float *src, const float *gain,
         }
         amax = warp_max(amax);
         const float sc = __fdiv_rn(amax, 127.0f);
+        const float rinv = __frcp_rn(sc);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (j < epl) codes[base + j] = (int8_t)((sc == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v[j], sc)));
+            if (j < epl) codes[base + j] = (int8_t)((sc == 0.0f) ? 0 : q80_code(v[j], sc, rinv));
         }
         if (lane == 0) scales[gi] = sc;
     }
@@ -189,124 +254,20 @@ __device__ __forceinline__ void q80_load_smem(Q80Tile<2> &t, const unsigned char
     }
 }
 
-// ---------------------------------------------------------------- attention partial of one (kv head, split) from smem q/k/v
-// part layout per (kv head g, split): [KVM][hd + 2] floats: acc[hd], m, l
-template <int KVM, int NT>
-__device__ __forceinline__ void cl_attn_partial(const ClusterArgs &g, uint32_t layer, uint32_t kvh, uint32_t split, uint32_t rpk, uint32_t pos,
-                                                uint32_t range, const float *q_s, const float *kraw_s, const float *vrow_s, float *part_slot,
-                                                float *ws) {
-    constexpr int NW = NT / 32;
-    const Dims &d = g.d;
-    const uint32_t hd = d.hd;
-    uint32_t chunk = (range + rpk - 1) / rpk;
-    chunk = (chunk + 7u) & ~7u;
-    const uint32_t t0 = min(range, split * chunk), t1 = min(range, t0 + chunk), len = t1 - t0;
-    const bool owner = (pos >= t0 && pos < t1);
-    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
-    const uint32_t rpw = 32 / lpr;
-    // workspace: qs[KVM*hd] | krow[hd] | stat[2*KVM] (+pad) | sc[KVM*cap] | red part[NW*rpw*KVM*hd]
-    float *qs = ws;
-    float *krow = qs + KVM * hd;
-    float *stat = krow + hd;
-    float *sc = stat + ((2 * KVM + 3) & ~3);
-    const uint32_t cap = (chunk + 7u) & ~7u;
-    float *part = sc + KVM * cap;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sub = lane / lpr, li = lane % lpr;
-    const float *cr = g.rope_cos + (size_t)pos * (hd / 2), *ci = g.rope_sin + (size_t)pos * (hd / 2);
-    const float *qn = g.qnorm ? g.qnorm + (size_t)layer * hd : nullptr, *kn = g.knorm ? g.knorm + (size_t)layer * hd : nullptr;
-
-    for (uint32_t i = threadIdx.x; i < KVM * hd; i += NT) qs[i] = q_s[(size_t)kvh * KVM * hd + i];
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) krow[i] = kraw_s[(size_t)kvh * hd + i];
-    __syncthreads();
-    for (uint32_t m = warp; m < KVM + (owner ? 1u : 0u); m += NW) {
-        if (m < KVM) head_norm_rope(qs + m * hd, qn, cr, ci, d, false);
-        else head_norm_rope(krow, kn, cr, ci, d, false);
-    }
-    __syncthreads();
-    const size_t kvl = (size_t)d.KV * d.max_seq * hd;
-    float *kbase = g.kc + layer * kvl + (size_t)kvh * d.max_seq * hd, *vbase = g.vc + layer * kvl + (size_t)kvh * d.max_seq * hd;
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) kbase[(size_t)pos * hd + i] = krow[i];
-    const float dv = sqrtf((float)hd);
-    const uint32_t col = li * 4;
-    const bool colon = col < hd;
-    float4 qv[KVM];
-#pragma unroll
-    for (int m = 0; m < KVM; m++) qv[m] = colon ? *reinterpret_cast<const float4 *>(qs + m * hd + col) : make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
-        const uint32_t tl = tb + sub;
-        float4 kv = make_float4(0, 0, 0, 0);
-        if (tl < len && colon) {
-            const uint32_t t = t0 + tl;
-            kv = (t == pos) ? *reinterpret_cast<const float4 *>(krow + col) : __ldcg(reinterpret_cast<const float4 *>(kbase + (size_t)t * hd + col));
-        }
-#pragma unroll
-        for (int m = 0; m < KVM; m++) {
-            float acc = kv.x * qv[m].x;
-            acc = fmaf(kv.y, qv[m].y, acc); acc = fmaf(kv.z, qv[m].z, acc); acc = fmaf(kv.w, qv[m].w, acc);
-            for (uint32_t o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (tl < len && li == 0) sc[m * cap + tl] = __fdiv_rn(acc, dv);
-        }
-    }
-    __syncthreads();
-    if (warp < KVM) {
-        float *s = sc + warp * cap;
-        float mx = -FLT_MAX;
-        for (uint32_t t = lane; t < len; t += 32) mx = fmaxf(mx, s[t]);
-        mx = warp_max(mx);
-        float ls = 0.0f;
-        for (uint32_t t = lane; t < len; t += 32) { const float e = expf(s[t] - mx); s[t] = e; ls += e; }
-        ls = warp_sum(ls);
-        if (lane == 0) { stat[2 * warp] = mx; stat[2 * warp + 1] = ls; }
-    }
-    __syncthreads();
-    float4 av[KVM];
-#pragma unroll
-    for (int m = 0; m < KVM; m++) av[m] = make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
-        const uint32_t tl = tb + sub;
-        if (tl < len && colon) {
-            const uint32_t t = t0 + tl;
-            const float4 vv = (t == pos) ? *reinterpret_cast<const float4 *>(vrow_s + (size_t)kvh * hd + col)
-                                         : __ldcg(reinterpret_cast<const float4 *>(vbase + (size_t)t * hd + col));
-#pragma unroll
-            for (int m = 0; m < KVM; m++) {
-                const float e = sc[m * cap + tl];
-                av[m].x = fmaf(e, vv.x, av[m].x); av[m].y = fmaf(e, vv.y, av[m].y);
-                av[m].z = fmaf(e, vv.z, av[m].z); av[m].w = fmaf(e, vv.w, av[m].w);
-            }
-        }
-    }
-    if (colon) {
-#pragma unroll
-        for (int m = 0; m < KVM; m++)
-            *reinterpret_cast<float4 *>(part + ((size_t)(warp * rpw + sub) * KVM + m) * hd + col) = av[m];
-    }
-    __syncthreads();
-    const uint32_t np = NW * rpw;
-    // reduce across warps and publish the partial to every CTA of the cluster; one warp handles one (m, i) element batch
-    for (uint32_t idx = warp; idx < KVM * (hd + 2); idx += NW) {
-        const uint32_t m = idx / (hd + 2), i = idx % (hd + 2);
-        float v;
-        if (i < hd) { v = 0.0f; for (uint32_t p = 0; p < np; p++) v += part[((size_t)p * KVM + m) * hd + i]; }
-        else v = (len == 0) ? (i == hd ? -FLT_MAX : 0.0f) : stat[2 * m + (i - hd)];
-        scatter_f32(part_slot + (size_t)m * (hd + 2) + i, v);
-    }
-}
-
 // ---------------------------------------------------------------- the kernel
 template <int LPG, int KVM>
 __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArgs g) {
     extern __shared__ __align__(128) unsigned char csm[];
     unsigned char *sm = csm;
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ volatile uint32_t stage_tile[kMaxStages];
     __shared__ MatvecSmem ms;
     constexpr uint32_t gs = LPG * 16;
     const Dims &d = g.d;
     const uint32_t rank = cluster_rank();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    Ring ring{full_bar, empty_bar, sm + g.off_ring, g.nstages, g.stage_bytes};
+    Ring ring{stage_tile, full_bar, empty_bar, sm + g.off_ring, g.nstages, g.stage_bytes};
     ClPhase *ph = reinterpret_cast<ClPhase *>(sm + g.off_phases);
     float *x_s = reinterpret_cast<float *>(sm + g.off_x), *q_s = reinterpret_cast<float *>(sm + g.off_q);
     float *kraw_s = reinterpret_cast<float *>(sm + g.off_kraw), *vrow_s = reinterpret_cast<float *>(sm + g.off_vrow);
@@ -317,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
     float *attn_ws = reinterpret_cast<float *>(sm + g.off_attn);
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kWarps); }
+        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); stage_tile[s] = 0xffffffffu; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -334,13 +295,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
     const float pen = __ldcg(&g.st->penalty);
     uint32_t tok = __ldcg(&g.st->use_token) ? __ldcg(&g.st->token) : __ldcg(g.ids + pos);
 
-    Producer prod{0, (uint64_t)g.n_steps * g.tiles_per_token, 0, 0, ph[0].has_gain ? -1 : 0};
+    Producer prod{0, g.n_steps * g.tiles_per_token, 0, 1u, 0, 0, nullptr, 0};      // parity 1 passes at once on a stage's first use
+    producer_enter_phase(g, ph, prod, rank);
     const uint32_t rpk = kCluster / d.KV;                 // ranks per kv head
     const uint32_t part_stride = KVM * (d.hd + 2);
 
+    uint32_t ti = 0;
     for (uint32_t step = 0; step < g.n_steps; step++) {
-        const uint64_t tok_tile0 = (uint64_t)step * g.tiles_per_token;
-        if (warp == 0 && lane == 0) ring_refill(g, ph, ring, prod, tok_tile0, rank);      // start streaming before the embedding fetch
+        const uint32_t tok_tile0 = step * g.tiles_per_token;
+        CL_STAMP();
+        if (warp == 0 && lane == 0) produce(g, ph, ring, prod, prod.total, false, rank);   // keep the ring full across the token boundary
         embed_row<kThreads>(g.emb_w, g.emb_aux, x_s, tok, d);
         __syncthreads();
         const uint32_t range = causal ? pos + 1 : d.max_seq;
@@ -350,67 +314,69 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
             const ClPhase &c = ph[p];
             const uint32_t G = c.n / gs;
             const float *src = (c.pad == 1u) ? xba_s : (c.pad == 2u) ? hb_s : x_s;       // pad = activation source selector
-            uint64_t t = tok_tile0 + c.tile_base;
+            const uint32_t t_hdr = tok_tile0 + c.tile_base;
+            const uint32_t t0w = t_hdr + (c.has_gain ? 1u : 0u);          // first weight tile of the phase
             // ---- header tile (gain) + activation prologue ----
             const float *gain = nullptr;
             uint32_t hs = 0;
             if (c.has_gain) {
-                hs = (uint32_t)(t % ring.nstages);
-                if (warp == 0 && lane == 0) ring_refill(g, ph, ring, prod, t, rank);
-                mbar_wait(&ring.full[hs], (uint32_t)(t / ring.nstages) & 1u);
+                if (warp == 0 && lane == 0) produce(g, ph, ring, prod, t_hdr + 1, true, rank);
+                hs = ring_wait_tile(ring, t_hdr);
                 gain = reinterpret_cast<const float *>(ring.buf + (size_t)hs * ring.stage_bytes);
             }
-            cl_prep_q80<kThreads>(src, gain, (int)c.n, (int)gs, act, ms.red);
-            if (c.has_gain) { if (lane == 0) mbar_arrive(&ring.empty[hs]); t++; }
-            // ---- weight tiles ----
-            const uint32_t ppt = c.rows_per_tile / 2;                 // row pairs per full tile
-            for (uint32_t j = 0; j < c.ntiles; j++, t++) {
-                const uint32_t s = (uint32_t)(t % ring.nstages);
-                if (warp == 0 && lane == 0) ring_refill(g, ph, ring, prod, t, rank);
-                mbar_wait(&ring.full[s], (uint32_t)(t / ring.nstages) & 1u);
-                const uint32_t rows = min(c.rows_per_tile, c.rows_per_rank - j * c.rows_per_tile);
-                const unsigned char *tile = ring.buf + (size_t)s * ring.stage_bytes;
-                const float *tscales = reinterpret_cast<const float *>(tile + (size_t)rows * c.n);
-                const uint32_t first = (uint32_t)((warp + kWarps - (j * ppt) % kWarps) % kWarps);
-                for (uint32_t i = first; i < rows / 2; i += kWarps) {
-                    float val[2] = {0.0f, 0.0f};
-                    for (uint32_t k0 = 0; k0 < c.n; k0 += 1024) {
-                        Q80Tile<2> tl;
-                        q80_load_smem<LPG>(tl, tile + (size_t)(2 * i) * c.n, tscales + (size_t)(2 * i) * G, c.n, k0);
-                        q80_consume<2, LPG>(tl, c.n, k0, act, val);
-                    }
-                    const uint32_t lrow = j * c.rows_per_tile + 2 * i;           // row within this rank's slice
-                    const uint32_t row = rank * c.rows_per_rank + lrow;          // row of the fused matrix
-                    if (c.epi == EPI_SWIGLU) {
-                        const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val[0])));
-                        scatter_f32(hb_s + (row >> 1), __fmul_rn(__fmul_rn(val[0], sg), val[1]));
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            const uint32_t rr = row + r;
-                            float v = val[r];
-                            if (c.epi == EPI_RESID) scatter_f32(x_s + rr, __fadd_rn(x_s[rr], v));
-                            else if (c.epi == EPI_QKV) {
-                                if (rr < d.q_dim) scatter_f32(q_s + rr, v);
-                                else if (rr < d.q_dim + d.kv_dim) scatter_f32(kraw_s + (rr - d.q_dim), v);
-                                else {
-                                    const uint32_t cc = rr - d.q_dim - d.kv_dim, h = cc / d.hd, e = cc % d.hd;
-                                    scatter_f32(vrow_s + cc, v);
-                                    if (lane == 0) g.vc[(size_t)c.layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + e] = v;
-                                }
-                            } else {        // EPI_CLS: infer.c:1156-1167 penalty, then first-max argmax :1026-1037
-                                if (pen != 1.0f && __ldcg(g.seen + rr)) v = __fdiv_rn(v, pen);
-                                if (lane == 0) g.logits[rr] = v;
-                                if (v > bestv) { bestv = v; besti = rr; }
-                            }
-                        }
-                    }
+            cl_prep_q80<kThreads>(src, gain, (int)c.n, (int)gs, act, ms.red);        // ends with __syncthreads()
+            if (c.has_gain && threadIdx.x == 32) mbar_arrive(&ring.empty[hs]);
+            CL_STAMP();
+            // ---- weight tiles: warp 0 streams, warps 1..15 each own whole tiles (one lane per row) ----
+            if (warp == 0) {
+                if (lane == 0) {
+                    produce(g, ph, ring, prod, t0w + c.ntiles, true, rank);          // everything this phase needs
+                    produce(g, ph, ring, prod, prod.total, false, rank);             // and whatever later phases fit
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ring.empty[s]);
+            } else {
+                for (uint32_t j = (uint32_t)warp - 1; j < c.ntiles; j += kWarps - 1) {
+                    const uint32_t s = ring_wait_tile(ring, t0w + j);
+                    const uint32_t rows = min(c.rows_per_tile, c.rows_per_rank - j * c.rows_per_tile);
+                    const unsigned char *tile = ring.buf + (size_t)s * ring.stage_bytes;
+                    const float *tscales = reinterpret_cast<const float *>(tile + (size_t)rows * c.row_stride);
+                    const bool on = (uint32_t)lane < rows;
+                    float v = 0.0f;
+                    if (on) v = cl_row_dot<LPG>(tile + (size_t)lane * c.row_stride, tscales + (size_t)lane * c.gs_stride, c.n, act);
+                    // release the stage before the epilogue (the arrive has release semantics; DSMEM stores issued before it
+                    // would have to be acknowledged by 16 SMs first)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ring.empty[s]);
+                    const uint32_t row = rank * c.rows_per_rank + j * c.rows_per_tile + (uint32_t)lane;   // row of the fused matrix
+                    if (c.epi == EPI_SWIGLU) {            // lanes (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
+                        const float v3 = __shfl_down_sync(0xffffffffu, v, 1);
+                        const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+                        scatter_lane_f32(hb_s + (row >> 1), __fmul_rn(__fmul_rn(v, sg), v3), on && !(lane & 1));
+                    } else if (c.epi == EPI_RESID) {
+                        scatter_lane_f32(x_s + row, on ? __fadd_rn(x_s[row], v) : 0.0f, on);
+                    } else if (c.epi == EPI_QKV) {
+                        float *dst = q_s + row;
+                        if (row >= d.q_dim + d.kv_dim) {
+                            const uint32_t cc = row - d.q_dim - d.kv_dim, h = cc / d.hd, e = cc % d.hd;
+                            dst = vrow_s + cc;
+                            if (on) g.vc[(size_t)c.layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + e] = v;
+                        } else if (row >= d.q_dim) dst = kraw_s + (row - d.q_dim);
+                        scatter_lane_f32(dst, v, on);
+                    } else if (on) {       // EPI_CLS: infer.c:1156-1167 penalty, then first-max argmax :1026-1037 (rows ascend per lane)
+                        if (pen != 1.0f && __ldcg(g.seen + row)) v = __fdiv_rn(v, pen);
+                        g.logits[row] = v;
+                        if (v > bestv) { bestv = v; besti = row; }
+                    }
+                }
             }
+            CL_STAMP();
             // ---- phase boundary ----
             if (c.epi == EPI_CLS) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bestv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                    if (oi != 0xffffffffu && (ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+                }
                 if (lane == 0) { ms.best_v[warp] = bestv; ms.best_i[warp] = besti; }
                 __syncthreads();
                 if (warp == 0) {
@@ -426,12 +392,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
                 }
             }
             cluster_sync_all();
+            CL_STAMP();
             if (c.epi == EPI_QKV) {
                 // ---- attention: this rank's (kv head, split) partial -> all replicas; then every CTA merges all heads ----
                 const uint32_t kvh = rank / rpk, split = rank % rpk;
-                cl_attn_partial<KVM, kThreads>(g, c.layer, kvh, split, rpk, pos, range, q_s, kraw_s, vrow_s,
-                                               part_s + (size_t)(kvh * rpk + split) * part_stride, attn_ws);
+                {
+                    uint32_t chunk = (range + rpk - 1) / rpk;
+                    chunk = (chunk + 7u) & ~7u;
+                    const uint32_t at0 = min(range, split * chunk), at1 = min(range, at0 + chunk);
+                    const size_t kvl = (size_t)d.KV * d.max_seq * d.hd;
+                    float *kb = g.kc + c.layer * kvl + (size_t)kvh * d.max_seq * d.hd;
+                    const float *vb = g.vc + c.layer * kvl + (size_t)kvh * d.max_seq * d.hd;
+                    float *outp = attn_ws + (size_t)kWarps * KVM * (d.hd + 4);
+                    attn_stream_partial<KVM, kThreads, false>(d, q_s + (size_t)kvh * KVM * d.hd, kraw_s + (size_t)kvh * d.hd, vrow_s + (size_t)kvh * d.hd, kb, vb,
+                                                              g.qnorm ? g.qnorm + (size_t)c.layer * d.hd : nullptr, g.knorm ? g.knorm + (size_t)c.layer * d.hd : nullptr,
+                                                              g.rope_cos + (size_t)pos * (d.hd / 2), g.rope_sin + (size_t)pos * (d.hd / 2), pos, at0, at1 - at0, attn_ws, outp,
+                                                              (g.trace && rank == 0 && step + 1 == g.n_steps && c.layer == d.L / 2) ? g.trace + 1040 : nullptr);
+                    float *slot = part_s + (size_t)(kvh * rpk + split) * part_stride;
+                    for (uint32_t idx = warp; idx < part_stride; idx += kWarps) scatter_f32(slot + idx, outp[idx]);
+                }
+                CL_STAMP();
                 cluster_sync_all();
+                CL_STAMP();
                 for (uint32_t idx = threadIdx.x; idx < d.H * d.hd; idx += kThreads) {
                     const uint32_t h = idx / d.hd, i = idx % d.hd, kh = h / KVM, m = h % KVM;
                     float M = -FLT_MAX;
@@ -446,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
                     xba_s[idx] = __fdiv_rn(o, L);
                 }
                 __syncthreads();
+                CL_STAMP();
             }
         }
         // ---- every CTA knows all 16 partial argmaxes: pick the token, advance the state ----

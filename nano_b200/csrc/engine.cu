@@ -258,7 +258,7 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.st = e->st; a.nsplit_max = e->nsplit_max; a.chunk_cap = e->chunk_cap; a.d = d;
         void (*kern)(const AttnArgs) = k_attention;
         uint32_t smem = e->attn_smem;
-        if (d.hd <= 128 && !getenv("NB200_GENERIC_ATTN")) {
+        if (d.hd <= 128 && (d.arch != 3u || (d.hd & (d.hd - 1)) == 0) && !getenv("NB200_GENERIC_ATTN")) {
             switch (d.kv_mul) {
                 case 1: kern = k_attention_fast<1>; break;
                 case 2: kern = k_attention_fast<2>; break;
@@ -332,7 +332,7 @@ MegaKern pick_mega_kvm(uint32_t kvm) {
 }
 
 MegaKern pick_mega(const Dims &d) {
-    if (d.hd > 128) return nullptr;
+    if (d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0)) return nullptr;     // in-register half-split RoPE needs hd = 4 * 2^k
     if (d.quant == 0x00u) return pick_mega_kvm<0x00, 8>(d.kv_mul);
     if (d.quant == 0x42u) return pick_mega_kvm<0x42, 8>(d.kv_mul);
     if (d.gs == 128) return pick_mega_kvm<0x80, 8>(d.kv_mul);
@@ -364,7 +364,7 @@ int launch_mega(nb200_engine *e, uint32_t n_steps) {
 int launch_cluster(nb200_engine *e, uint32_t n_steps) {
     if (n_steps == 0) return 0;
     ClusterArgs g = e->cl;
-    g.n_steps = n_steps;
+    g.n_steps = n_steps; g.trace = e->trace_dev;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(kCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = e->cl_smem; cfg.stream = e->stream;
     cudaLaunchAttribute attr[1];
@@ -451,21 +451,20 @@ int put_rows(nb200_engine *e, Mat &m, const uint8_t *w, const uint8_t *aux, uint
 }
 
 // ---------------- cluster-resident path: weight stream + schedule ----------------
-// copy one fused Q80 matrix into the per-rank tile stream: tile = [rows x n codes][rows x G scales]
+// copy one fused Q80 matrix into the per-rank tile stream: tile = [rows x (n+16) codes, rows padded][rows x gs_stride scales]
 __global__ void k_build_stream(const uint8_t *__restrict__ codes, const float *__restrict__ scales, uint32_t rows_per_rank, uint32_t n, uint32_t G,
-                               uint32_t T, uint32_t tile_stride, uint8_t *stream, uint64_t rank_stride, uint64_t phase_off) {
+                               uint32_t T, uint32_t tile_stride, uint32_t row_stride, uint32_t gs_stride, uint8_t *stream, uint64_t rank_stride,
+                               uint64_t phase_off) {
     const uint32_t rank = blockIdx.y;
-    const uint32_t chunks_per_row = n / 16 + (G * 4 + 15) / 16;       // 16-byte chunks of codes, then of scales (scales copied per float below)
-    (void)chunks_per_row;
     for (uint32_t lrow = blockIdx.x; lrow < rows_per_rank; lrow += gridDim.x) {
         const uint32_t j = lrow / T, i = lrow % T;
         const uint32_t rows = min(T, rows_per_rank - j * T);
         uint8_t *tile = stream + (uint64_t)rank * rank_stride + phase_off + (uint64_t)j * tile_stride;
         const uint64_t grow = (uint64_t)rank * rows_per_rank + lrow;
         const int4 *src = reinterpret_cast<const int4 *>(codes + grow * n);
-        int4 *dst = reinterpret_cast<int4 *>(tile + (uint64_t)i * n);
+        int4 *dst = reinterpret_cast<int4 *>(tile + (uint64_t)i * row_stride);
         for (uint32_t c = threadIdx.x; c < n / 16; c += blockDim.x) dst[c] = src[c];
-        float *sdst = reinterpret_cast<float *>(tile + (uint64_t)rows * n) + (uint64_t)i * G;
+        float *sdst = reinterpret_cast<float *>(tile + (uint64_t)rows * row_stride) + (uint64_t)i * gs_stride;
         for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) sdst[c] = scales[grow * G + c];
     }
 }
@@ -484,7 +483,7 @@ ClusterKern pick_cluster_kvm(uint32_t kvm) {
 // returns 0 and sets e->use_cluster when the model fits the cluster-resident kernel; 0 without setting it otherwise
 int setup_cluster(nb200_engine *e) {
     const Dims &d = e->d;
-    if (d.quant != 0x80u || d.exact || d.hd > 128 || (d.gs != 64 && d.gs != 128) || d.KV > (uint32_t)kCluster || kCluster % d.KV) return 0;
+    if (d.quant != 0x80u || d.exact || d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0) || (d.gs != 64 && d.gs != 128) || d.KV > (uint32_t)kCluster || kCluster % d.KV) return 0;
     ClusterKern k = (d.gs == 128) ? pick_cluster_kvm<8>(d.kv_mul) : pick_cluster_kvm<4>(d.kv_mul);
     if (!k) return 0;
     const uint32_t L = d.L, E = d.E, QD = d.q_dim, KD = d.kv_dim, F = d.F, V = d.V;
@@ -501,20 +500,22 @@ int setup_cluster(nb200_engine *e) {
     (void)QD; (void)KD; (void)F; (void)V;
 
     // stage size and per-phase tile geometry
-    const uint32_t stage_cap = 34 * 1024;
+    const char *sc_env = getenv("NB200_STAGE_KB");
+    const uint32_t stage_cap = (sc_env ? (uint32_t)atoi(sc_env) : 26u) * 1024u + 512u;
     uint32_t stage_bytes = (E * 4 + 127) & ~127u;
     std::vector<ClPhase> ph(pms.size());
     uint64_t off = 0; uint32_t tile_idx = 0;
     for (size_t i = 0; i < pms.size(); i++) {
         const Mat &m = *pms[i].m;
-        const uint32_t G = m.n / d.gs, rpr = m.rows / kCluster, rowb = m.n + 4 * G;
-        uint32_t T = stage_cap / rowb; T &= ~1u; if (T > 32) T = 32; if (T > rpr) T = rpr; if (T < 2) return 0;
+        const uint32_t G = m.n / d.gs, rpr = m.rows / kCluster, row_stride = m.n + 16u, gs_stride = G | 1u, rowb = row_stride + 4u * gs_stride;
+        uint32_t T = 32; while (T > 2 && T * rowb > stage_cap) T >>= 1;      // one lane per row: 32, 16, 8 ... rows per tile
+        if (T * rowb > stage_cap) return 0;
         const uint32_t tstride = (T * rowb + 15u) & ~15u;
         if (tstride > stage_bytes) stage_bytes = (tstride + 127u) & ~127u;
         ClPhase &c = ph[i];
         memset(&c, 0, sizeof c);
         c.stream_off = off; c.has_gain = pms[i].has_gain; c.rows_per_rank = rpr; c.rows_per_tile = T; c.tile_stride = tstride;
-        c.n = m.n; c.epi = pms[i].epi; c.layer = pms[i].layer; c.pad = pms[i].src_sel;
+        c.n = m.n; c.epi = pms[i].epi; c.layer = pms[i].layer; c.pad = pms[i].src_sel; c.row_stride = row_stride; c.gs_stride = gs_stride;
         c.ntiles = (rpr + T - 1) / T;
         c.tile_base = tile_idx; tile_idx += c.ntiles + (c.has_gain ? 1u : 0u);
         c.gain_off = (pms[i].epi == EPI_QKV) ? (uint64_t)pms[i].layer * E * 4
@@ -529,8 +530,8 @@ int setup_cluster(nb200_engine *e) {
     const uint32_t rpk = kCluster / d.KV;
     uint32_t lpr = 1; while (lpr * 4 < d.hd) lpr <<= 1;
     const uint32_t rpw = 32 / lpr;
-    uint32_t capmax = (d.max_seq + rpk - 1) / rpk; capmax = (capmax + 7u) & ~7u; capmax = (capmax + 7u) & ~7u;
-    const uint32_t attn_floats = d.kv_mul * d.hd + d.hd + ((2 * d.kv_mul + 3) & ~3u) + d.kv_mul * capmax + kWarps * rpw * d.kv_mul * d.hd + 16;
+    (void)rpw;
+    const uint32_t attn_floats = attn_stream_ws_floats(d.kv_mul, d.hd, kWarps);
     uint32_t maxn = E; if (d.q_dim > maxn) maxn = d.q_dim; if (d.F > maxn) maxn = d.F;
     uint32_t o = 0;
     ClusterArgs &g = e->cl;
@@ -581,7 +582,7 @@ int setup_cluster(nb200_engine *e) {
         const ClPhase &c = ph[i];
         uint32_t gx = c.rows_per_rank < 1024 ? c.rows_per_rank : 1024;
         k_build_stream<<<dim3(gx, kCluster), 128>>>((const uint8_t *)m.w, (const float *)m.aux, c.rows_per_rank, m.n, m.n / d.gs, c.rows_per_tile,
-                                                  c.tile_stride, stream, rank_stride, c.stream_off);
+                                                  c.tile_stride, c.row_stride, c.gs_stride, stream, rank_stride, c.stream_off);
         CK(cudaGetLastError());
     }
     CK(cudaDeviceSynchronize());
@@ -1060,7 +1061,7 @@ int nb200_profile_tokens(nb200_engine *e, const uint32_t *ids, uint32_t start, u
 // Debug: per-barrier clock64() stamps of CTA 0 for one token through the persistent kernel (5L+3 stamps + 1).
 int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned long long *stamps, uint32_t cap, uint32_t *count) {
     if (!e || !stamps || !count) return fail(NB200_EINVAL, "null argument");
-    if (!e->use_mega) return fail(NB200_EINVAL, "persistent kernel not active");
+    if (!e->use_mega && !e->use_cluster) return fail(NB200_EINVAL, "persistent kernel not active");
     CK(cudaSetDevice(e->device));
     const uint32_t n = 1024 + 64;          // [0, 5L+4): per-barrier stamps; [1024, 1024+48): intra-phase stamps of layer L/2
     if (cap < n || 5 * e->d.L + 4 > 1024) return fail(NB200_EINVAL, "need room for %u stamps", n);
@@ -1069,7 +1070,7 @@ int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned lo
     CK(cudaMemset(buf, 0, (size_t)n * 8));
     e->trace_dev = buf;
     int r = push_state(e, pos, 1, 0, 0, 1.0f, token, 1);
-    if (!r) r = launch_mega(e, 1);
+    if (!r) r = e->use_cluster ? launch_cluster(e, 1) : launch_mega(e, 1);
     e->trace_dev = nullptr;
     cudaStreamSynchronize(e->stream);
     if (!r) { CK(cudaMemcpy(stamps, buf, (size_t)n * 8, cudaMemcpyDeviceToHost)); *count = n; }

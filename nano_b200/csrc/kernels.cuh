@@ -201,6 +201,17 @@ __device__ void prep_f32(const float *src, const float *__restrict__ gain, int n
     __syncthreads();
 }
 
+// (int8) round(x / scale) of tensor.c:40-42, bit-exact with a fast path: q = x * (1/scale) is within ~4e-5 of the
+// correctly rounded quotient for |q| <= 127, so unless q sits within 1e-3 of a .5 boundary the rounded integer is
+// unambiguous; the rare boundary case takes the IEEE division + roundf path.
+__device__ __forceinline__ int q80_code(float v, float sc, float rinv) {
+    const float q = v * rinv;
+    const float a = fabsf(q), fl = floorf(a), frac = a - fl;
+    if (fabsf(frac - 0.5f) < 1e-3f) return (int)roundf(__fdiv_rn(v, sc));
+    const int c = (int)fl + (frac > 0.5f ? 1 : 0);
+    return q < 0.0f ? -c : c;
+}
+
 // tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
 template <int NT>
 __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n, int gs, bool exact,
@@ -225,12 +236,10 @@ __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n
         }
         amax = warp_max(amax);
         const float sc = __fdiv_rn(amax, 127.0f);
+        const float rinv = __frcp_rn(sc);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            if (j < epl) {
-                int c = (sc == 0.0f) ? 0 : (int)roundf(__fdiv_rn(v[j], sc));
-                codes[base + j] = (int8_t)c;
-            }
+            if (j < epl) codes[base + j] = (int8_t)((sc == 0.0f) ? 0 : q80_code(v[j], sc, rinv));
         }
         if (lane == 0) scales[g] = sc;
     }
@@ -828,16 +837,205 @@ __device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict
     __syncwarp();
 }
 
-// Fast path (hd <= 128, kv_mul in {1,2,4,8}): one CTA = (kv head g, split).  K and V rows are read once for
-// all KVM query heads of the group; softmax statistics are per-warp (no block barriers); the last CTA of
-// the kv head merges the splits with all threads.
-// smem (floats): qs[KVM*hd] | krow[hd] | sc[KVM*chunk_cap] | wsc[KVM*nsplit_max] | stat[2*KVM] | part[8*rpw*KVM*hd]
+// ------------------------------------------------------------------------------------------------
+// Streaming (online-softmax) attention partial for one (kv head, range of positions), hd <= 128.
+//   * every lane group (lpr lanes = one cache row) keeps its own running (max, sum, acc) for the KVM query heads of
+//     the kv head: no score buffer, no block-wide softmax; K and V rows of a batch are requested together before any
+//     is consumed (memory-level parallelism);
+//   * q (and the position's k) are normalised + RoPE'd in registers by every lane group: no staging, no barriers;
+//   * slots are merged with xor-shuffles inside a warp, then across warps through shared memory.
+// Result (un-normalised): outp[m*(hd+2) + i] = sum_t e^{s_t - M} v_t[i],  outp[.. + hd] = M,  outp[.. + hd+1] = sum_t e^{s_t - M}.
+// ------------------------------------------------------------------------------------------------
+// per-warp rows of the workspace are (hd + 4) floats apart so the float4 stores stay 16-byte aligned for any hd % 4 == 0
+__host__ __device__ inline uint32_t attn_stream_ws_floats(uint32_t kvm, uint32_t hd, uint32_t nwarps) { return nwarps * kvm * (hd + 4u) + kvm * (hd + 2u) + 16u; }
 __host__ __device__ inline uint32_t attn_fast_smem_floats(uint32_t kvm, uint32_t hd, uint32_t chunk_cap, uint32_t nsplit_max, uint32_t nwarps) {
-    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
-    const uint32_t rpw = 32 / lpr;
-    return kvm * hd + hd + kvm * chunk_cap + kvm * nsplit_max + 2 * kvm + 8 + nwarps * rpw * kvm * hd;
+    (void)chunk_cap;
+    return attn_stream_ws_floats(kvm, hd, nwarps) + kvm * nsplit_max + 2u * kvm + 16u;
 }
 
+// head-norm (Qwen3) + RoPE of the float4 slice a lane holds of one head vector (infer.c:814-835); lpr lanes = one vector
+__device__ __forceinline__ float4 norm_rope_slice(float4 v, const float *__restrict__ gain, const float *__restrict__ cr, const float *__restrict__ ci,
+                                                  const Dims &d, uint32_t lpr, uint32_t col, bool colon) {
+    if (d.arch == 3u) {
+        float ss = colon ? fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))) : 0.0f;
+        for (uint32_t o = lpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        ss = __fdiv_rn(ss, (float)d.hd);
+        ss = __fadd_rn(ss, 1e-5f);
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+        if (colon) {
+            const float4 gn = *reinterpret_cast<const float4 *>(gain + col);
+            v.x = __fmul_rn(gn.x, __fmul_rn(inv, v.x)); v.y = __fmul_rn(gn.y, __fmul_rn(inv, v.y));
+            v.z = __fmul_rn(gn.z, __fmul_rn(inv, v.z)); v.w = __fmul_rn(gn.w, __fmul_rn(inv, v.w));
+        }
+        // half-split pairs (i, i + hd/2): the partner element lives lpr/2 lanes away (hd == 4*lpr on this path)
+        const uint32_t half = d.hd / 2, hl = lpr >> 1;
+        float4 o4;
+        o4.x = __shfl_xor_sync(0xffffffffu, v.x, hl); o4.y = __shfl_xor_sync(0xffffffffu, v.y, hl);
+        o4.z = __shfl_xor_sync(0xffffffffu, v.z, hl); o4.w = __shfl_xor_sync(0xffffffffu, v.w, hl);
+        if (colon) {
+            const bool first = col < half;
+            const uint32_t i0 = first ? col : col - half;
+            const float4 c = *reinterpret_cast<const float4 *>(cr + i0), sn = *reinterpret_cast<const float4 *>(ci + i0);
+            if (first) {      // head[i] = v0*c - v1*s
+                v.x = __fsub_rn(__fmul_rn(v.x, c.x), __fmul_rn(o4.x, sn.x)); v.y = __fsub_rn(__fmul_rn(v.y, c.y), __fmul_rn(o4.y, sn.y));
+                v.z = __fsub_rn(__fmul_rn(v.z, c.z), __fmul_rn(o4.z, sn.z)); v.w = __fsub_rn(__fmul_rn(v.w, c.w), __fmul_rn(o4.w, sn.w));
+            } else {          // head[i + half] = v1*c + v0*s
+                v.x = __fadd_rn(__fmul_rn(v.x, c.x), __fmul_rn(o4.x, sn.x)); v.y = __fadd_rn(__fmul_rn(v.y, c.y), __fmul_rn(o4.y, sn.y));
+                v.z = __fadd_rn(__fmul_rn(v.z, c.z), __fmul_rn(o4.z, sn.z)); v.w = __fadd_rn(__fmul_rn(v.w, c.w), __fmul_rn(o4.w, sn.w));
+            }
+        }
+    } else if (colon) {        // adjacent pairs (2i, 2i+1): both pairs of the float4 are lane-local (infer.c:681-690)
+        const float c0 = cr[col / 2], s0 = ci[col / 2], c1 = cr[col / 2 + 1], s1 = ci[col / 2 + 1];
+        const float x = v.x, y = v.y, z = v.z, w = v.w;
+        v.x = __fsub_rn(__fmul_rn(x, c0), __fmul_rn(y, s0)); v.y = __fadd_rn(__fmul_rn(x, s0), __fmul_rn(y, c0));
+        v.z = __fsub_rn(__fmul_rn(z, c1), __fmul_rn(w, s1)); v.w = __fadd_rn(__fmul_rn(z, s1), __fmul_rn(w, c1));
+    }
+    return v;
+}
+
+template <int KVM, int NT, bool SRC_GLOBAL>
+__device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *q_src, const float *kraw_src, const float *vrow_src,
+                                                    float *kbase, const float *vbase, const float *qn, const float *kn,
+                                                    const float *cr, const float *ci, uint32_t pos, uint32_t t0, uint32_t len,
+                                                    float *ws, float *outp, unsigned long long *dbg = nullptr) {
+#define AT_STAMP(k) do { if (dbg && threadIdx.x == 0) dbg[k] = clock64(); } while (0)
+    constexpr int NW = NT / 32;
+    constexpr int U = 4;                          // cache rows (K and V) requested per lane group before any is consumed
+    AT_STAMP(0);         // cache rows (K and V) requested per lane group before any is consumed
+    const uint32_t hd = d.hd;
+    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
+    const uint32_t rpw = 32 / lpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sub = lane / lpr, li = lane % lpr, col = li * 4;
+    const bool colon = col < hd;
+    const float inv_dv = 1.0f / sqrtf((float)hd);   // fast mode: score * (1/sqrt(hd)) and __expf; exact mode has its own kernel
+
+    float4 qv[KVM];
+#pragma unroll
+    for (int m = 0; m < KVM; m++) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (colon) v = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(q_src + m * hd + col)) : *reinterpret_cast<const float4 *>(q_src + m * hd + col);
+        qv[m] = norm_rope_slice(v, qn, cr, ci, d, lpr, col, colon);
+    }
+    float mx[KVM], ls[KVM]; float4 av[KVM];
+#pragma unroll
+    for (int m = 0; m < KVM; m++) { mx[m] = -FLT_MAX; ls[m] = 0.0f; av[m] = make_float4(0, 0, 0, 0); }
+    AT_STAMP(1);
+
+    const uint32_t stride = NW * rpw;
+    for (uint32_t tb0 = warp * rpw; tb0 < len; tb0 += stride * U) {
+        float4 kr[U], vr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t tl = tb0 + u * stride + sub, t = t0 + tl;
+            kr[u] = make_float4(0, 0, 0, 0); vr[u] = make_float4(0, 0, 0, 0);
+            if (tl < len && colon && t != pos) {
+                kr[u] = __ldcg(reinterpret_cast<const float4 *>(kbase + (size_t)t * hd + col));
+                vr[u] = __ldcg(reinterpret_cast<const float4 *>(vbase + (size_t)t * hd + col));
+            }
+        }
+        // scores of the whole batch first (independent shuffle-reductions), then ONE rescale of the running state
+        float scr[U][KVM];
+        bool vld[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t tl = tb0 + u * stride + sub, t = t0 + tl;
+            vld[u] = tl < len;
+            // the current position's row: k is normalised + roped here (and stored for later tokens), v comes from the step's own output
+            if (__any_sync(0xffffffffu, vld[u] && t == pos)) {
+                const bool mine = vld[u] && t == pos;
+                float4 kk = make_float4(0, 0, 0, 0);
+                if (mine && colon) kk = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(kraw_src + col)) : *reinterpret_cast<const float4 *>(kraw_src + col);
+                kk = norm_rope_slice(kk, kn, cr, ci, d, lpr, col, colon);      // executed by the whole warp (shuffles); only `mine` keeps it
+                if (mine && colon) {
+                    kr[u] = kk;
+                    *reinterpret_cast<float4 *>(kbase + (size_t)pos * hd + col) = kk;
+                    vr[u] = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(vrow_src + col)) : *reinterpret_cast<const float4 *>(vrow_src + col);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < KVM; m++) {
+                float sdot = kr[u].x * qv[m].x;
+                sdot = fmaf(kr[u].y, qv[m].y, sdot); sdot = fmaf(kr[u].z, qv[m].z, sdot); sdot = fmaf(kr[u].w, qv[m].w, sdot);
+                for (uint32_t o = lpr >> 1; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+                scr[u][m] = vld[u] ? sdot * inv_dv : -FLT_MAX;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < KVM; m++) {
+            float bm = scr[0][m];
+#pragma unroll
+            for (int u = 1; u < U; u++) bm = fmaxf(bm, scr[u][m]);
+            const float mn = fmaxf(mx[m], bm);
+            const float a = __expf(mx[m] - mn);
+            float l2 = ls[m] * a;
+            float4 a4 = make_float4(av[m].x * a, av[m].y * a, av[m].z * a, av[m].w * a);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const float pr = vld[u] ? __expf(scr[u][m] - mn) : 0.0f;
+                l2 += pr;
+                a4.x = fmaf(pr, vr[u].x, a4.x); a4.y = fmaf(pr, vr[u].y, a4.y); a4.z = fmaf(pr, vr[u].z, a4.z); a4.w = fmaf(pr, vr[u].w, a4.w);
+            }
+            ls[m] = l2; av[m] = a4; mx[m] = mn;
+        }
+    }
+    AT_STAMP(2);
+    // merge the row slots of a warp
+    for (uint32_t off = lpr; off < 32; off <<= 1) {
+#pragma unroll
+        for (int m = 0; m < KVM; m++) {
+            const float mo = __shfl_xor_sync(0xffffffffu, mx[m], off), lo = __shfl_xor_sync(0xffffffffu, ls[m], off);
+            float4 ao;
+            ao.x = __shfl_xor_sync(0xffffffffu, av[m].x, off); ao.y = __shfl_xor_sync(0xffffffffu, av[m].y, off);
+            ao.z = __shfl_xor_sync(0xffffffffu, av[m].z, off); ao.w = __shfl_xor_sync(0xffffffffu, av[m].w, off);
+            const float mn = fmaxf(mx[m], mo), a = __expf(mx[m] - mn), bsc = __expf(mo - mn);
+            ls[m] = ls[m] * a + lo * bsc;
+            av[m].x = av[m].x * a + ao.x * bsc; av[m].y = av[m].y * a + ao.y * bsc;
+            av[m].z = av[m].z * a + ao.z * bsc; av[m].w = av[m].w * a + ao.w * bsc;
+            mx[m] = mn;
+        }
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int m = 0; m < KVM; m++) {
+            float *wp = ws + ((size_t)warp * KVM + m) * (hd + 4);
+            if (colon) *reinterpret_cast<float4 *>(wp + col) = av[m];
+            if (li == 0) { wp[hd] = mx[m]; wp[hd + 1] = ls[m]; }
+        }
+    }
+    AT_STAMP(3);
+    __syncthreads();
+    AT_STAMP(4);
+    // per (warp, head) weight e^{m_w - M}, computed once (slot hd+2 of the row), then a plain weighted sum per element
+    if (threadIdx.x < NW * KVM) {
+        const uint32_t m = threadIdx.x % KVM;
+        float M = -FLT_MAX;
+        for (int w = 0; w < NW; w++) M = fmaxf(M, ws[((size_t)w * KVM + m) * (hd + 4) + hd]);
+        float *wp = ws + (size_t)threadIdx.x * (hd + 4);          // threadIdx.x == w * KVM + m
+        wp[hd + 2] = __expf(wp[hd] - M);
+        wp[hd + 3] = M;
+    }
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < KVM * (hd + 2); idx += NT) {
+        const uint32_t m = idx / (hd + 2), i = idx % (hd + 2);
+        float r = 0.0f;
+        if (i == hd) r = ws[(size_t)m * (hd + 4) + hd + 3];
+        else {
+#pragma unroll 4
+            for (int w = 0; w < NW; w++) {
+                const float *wp = ws + ((size_t)w * KVM + m) * (hd + 4);
+                r = fmaf(wp[i < hd ? i : hd + 1], wp[hd + 2], r);
+            }
+        }
+        outp[idx] = r;
+    }
+    __syncthreads();
+    AT_STAMP(5);
+#undef AT_STAMP
+}
+
+// One (kv head, split) item of the grid-wide paths: partial -> HBM workspace; the last CTA of the kv head merges.
+// smem (floats): streaming workspace | wsc[KVM*nsplit_max] | stat[2*KVM]
 template <int KVM, int NT>
 __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_t split, uint32_t pos, uint32_t range, uint32_t chunk,
                                           uint32_t nsplit, float *sm, uint32_t &is_last) {
@@ -845,101 +1043,22 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
     const Dims &d = a.d;
     const uint32_t hd = d.hd;
     const uint32_t t0 = split * chunk, t1 = min(range, t0 + chunk), len = t1 - t0;
-    const bool owner = (pos >= t0 && pos < t1);
-    const uint32_t cap = a.chunk_cap;
-
-    uint32_t lpr = 1; while (lpr * 4 < hd) lpr <<= 1;
-    const uint32_t rpw = 32 / lpr;
-    float *qs = sm;
-    float *krow = qs + KVM * hd;
-    float *sc = krow + hd;
-    float *wsc = sc + KVM * cap;
+    float *ws = sm;
+    float *outp = ws + (size_t)NW * KVM * (hd + 4);
+    float *wsc = outp + KVM * (hd + 2);
     float *stat = wsc + KVM * a.nsplit_max;
-    float *part = sm + (((uint32_t)(stat - sm) + 2 * KVM + 3) & ~3u);       // 16-byte aligned
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sub = lane / lpr, li = lane % lpr;
     const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
-
-    for (uint32_t i = threadIdx.x; i < KVM * hd; i += NT) qs[i] = __ldcg(a.q + (size_t)g * KVM * hd + i);
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) krow[i] = __ldcg(a.kraw + (size_t)g * hd + i);
-    __syncthreads();
-    for (uint32_t m = warp; m < KVM + (owner ? 1u : 0u); m += NW) {
-        if (m < KVM) head_norm_rope(qs + m * hd, a.qnorm, cr, ci, d, false);
-        else head_norm_rope(krow, a.knorm, cr, ci, d, false);
-    }
-    __syncthreads();
     float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
-    if (owner) for (uint32_t i = threadIdx.x; i < hd; i += NT) kbase[(size_t)pos * hd + i] = krow[i];
-    const float dv = sqrtf((float)hd);
-    const uint32_t col = li * 4;
-    const bool colon = col < hd;
-
-    // ---- scores for all KVM heads from one pass over K ----
-    float4 qv[KVM];
-#pragma unroll
-    for (int m = 0; m < KVM; m++) qv[m] = colon ? *reinterpret_cast<const float4 *>(qs + m * hd + col) : make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
-        const uint32_t tl = tb + sub;
-        float4 kv = make_float4(0, 0, 0, 0);
-        if (tl < len && colon) {
-            const uint32_t t = t0 + tl;
-            kv = (t == pos) ? *reinterpret_cast<const float4 *>(krow + col)
-                            : __ldcg(reinterpret_cast<const float4 *>(kbase + (size_t)t * hd + col));
-        }
-#pragma unroll
-        for (int m = 0; m < KVM; m++) {
-            float acc = kv.x * qv[m].x;
-            acc = fmaf(kv.y, qv[m].y, acc); acc = fmaf(kv.z, qv[m].z, acc); acc = fmaf(kv.w, qv[m].w, acc);
-            for (uint32_t o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (tl < len && li == 0) sc[m * cap + tl] = __fdiv_rn(acc, dv);
-        }
-    }
-    __syncthreads();
-    // ---- per-head softmax statistics, one warp per head ----
-    if (warp < KVM) {
-        float *s = sc + warp * cap;
-        float mx = -FLT_MAX;
-        for (uint32_t t = lane; t < len; t += 32) mx = fmaxf(mx, s[t]);
-        mx = warp_max(mx);
-        float ls = 0.0f;
-        for (uint32_t t = lane; t < len; t += 32) { const float e = expf(s[t] - mx); s[t] = e; ls += e; }
-        ls = warp_sum(ls);
-        if (lane == 0) { stat[2 * warp] = mx; stat[2 * warp + 1] = ls; }
-    }
-    __syncthreads();
-    // ---- weighted V for all KVM heads from one pass over V ----
-    float4 av[KVM];
-#pragma unroll
-    for (int m = 0; m < KVM; m++) av[m] = make_float4(0, 0, 0, 0);
-    for (uint32_t tb = warp * rpw; tb < len; tb += NW * rpw) {
-        const uint32_t tl = tb + sub;
-        if (tl < len && colon) {
-            const float4 vv = __ldcg(reinterpret_cast<const float4 *>(vbase + (size_t)(t0 + tl) * hd + col));
-#pragma unroll
-            for (int m = 0; m < KVM; m++) {
-                const float e = sc[m * cap + tl];
-                av[m].x = fmaf(e, vv.x, av[m].x); av[m].y = fmaf(e, vv.y, av[m].y);
-                av[m].z = fmaf(e, vv.z, av[m].z); av[m].w = fmaf(e, vv.w, av[m].w);
-            }
-        }
-    }
-    if (colon) {
-#pragma unroll
-        for (int m = 0; m < KVM; m++)
-            *reinterpret_cast<float4 *>(part + ((size_t)(warp * rpw + sub) * KVM + m) * hd + col) = av[m];
-    }
-    __syncthreads();
-    const uint32_t np = NW * rpw;
+    attn_stream_partial<KVM, NT, true>(d, a.q + (size_t)g * KVM * hd, a.kraw + (size_t)g * hd, vbase + (size_t)pos * hd, kbase, vbase,
+                                       a.qnorm, a.knorm, cr, ci, pos, t0, len, ws, outp);
     for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
-        float s = 0.0f;
-        for (uint32_t p = 0; p < np; p++) s += part[((size_t)p * KVM + m) * hd + i];
-        a.ws_acc[((size_t)(g * KVM + m) * a.nsplit_max + split) * hd + i] = s;
+        a.ws_acc[((size_t)(g * KVM + m) * a.nsplit_max + split) * hd + i] = outp[m * (hd + 2) + i];
     }
     if (threadIdx.x < KVM) {
         const size_t slot = (size_t)(g * KVM + threadIdx.x) * a.nsplit_max + split;
-        a.ws_m[slot] = stat[2 * threadIdx.x]; a.ws_l[slot] = stat[2 * threadIdx.x + 1];
+        a.ws_m[slot] = outp[threadIdx.x * (hd + 2) + hd]; a.ws_l[slot] = outp[threadIdx.x * (hd + 2) + hd + 1];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -954,13 +1073,13 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
     if (warp < KVM) {
         const size_t base = (size_t)(g * KVM + warp) * a.nsplit_max;
         float M = -FLT_MAX;
-        for (uint32_t s = lane; s < nsplit; s += 32) M = fmaxf(M, __ldcg(a.ws_m + base + s));
+        for (uint32_t s2 = lane; s2 < nsplit; s2 += 32) M = fmaxf(M, __ldcg(a.ws_m + base + s2));
         M = warp_max(M);
         float L = 0.0f;
-        for (uint32_t s = lane; s < nsplit; s += 32) {
-            const float w = expf(__ldcg(a.ws_m + base + s) - M);
-            wsc[warp * a.nsplit_max + s] = w;
-            L += __ldcg(a.ws_l + base + s) * w;
+        for (uint32_t s2 = lane; s2 < nsplit; s2 += 32) {
+            const float w = expf(__ldcg(a.ws_m + base + s2) - M);
+            wsc[warp * a.nsplit_max + s2] = w;
+            L += __ldcg(a.ws_l + base + s2) * w;
         }
         L = warp_sum(L);
         if (lane == 0) stat[2 * warp] = L;
@@ -971,12 +1090,11 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
         const size_t base = (size_t)(g * KVM + m) * a.nsplit_max;
         float o = 0.0f;
 #pragma unroll 4
-        for (uint32_t s = 0; s < nsplit; s++) o = fmaf(__ldcg(a.ws_acc + (base + s) * hd + i), wsc[m * a.nsplit_max + s], o);
+        for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(__ldcg(a.ws_acc + (base + s2) * hd + i), wsc[m * a.nsplit_max + s2], o);
         a.xba[(size_t)(g * KVM + m) * hd + i] = __fdiv_rn(o, stat[2 * m]);
     }
     if (threadIdx.x == 0) a.ticket[g] = 0;
 }
-
 
 template <int KVM>
 __global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {      // same CTA shape as the megakernel => same bits
