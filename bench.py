@@ -238,7 +238,8 @@ def main():
     ap.add_argument("--exact", action="store_true", help="run the engine in exact (reference-order) mode")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-mega", action="store_true", help="multi-kernel CUDA-graph path instead of the persistent megakernel")
+    ap.add_argument("--no-mega", action="store_true", help="forbid the persistent megakernel")
+    ap.add_argument("--no-cluster", action="store_true", help="forbid the cluster-resident kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -258,7 +259,7 @@ def main():
     if dist is not None:
         dist.barrier()
     path = mf.cached_model(spec, quant, gs or 128)           # every rank finds the file rank 0 wrote
-    flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_MEGA if args.no_mega else 0)
+    flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_MEGA if args.no_mega else 0) | (E.FLAG_NO_CLUSTER if args.no_cluster else 0)
     eng = E.Engine(path, seq, device=local, flags=flags)
     n_dec = seq - PROMPT
 
@@ -359,7 +360,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"{args.workload} greedy decode, seq={seq}, prompt={PROMPT}, max_seq_len={seq}",
                    "parallelism": f"{world} independent batch-1 replica(s)", "mode": "exact" if args.exact else "fast",
-                   "engine": "multi-kernel graph" if (args.no_mega or args.exact) else "persistent megakernel (1 cooperative launch per run of tokens)",
+                   "engine": eng.path,
                    "l2": "inputs larger than L2: %.0f MB of weights (+KV) streamed per token vs 126 MB L2" % (eng.weight_bytes / 1e6),
                    "timing": "CUDA events around the decode segment of each step on the launching stream; max over ranks"},
         "clocks": clocks,

@@ -799,7 +799,12 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     CK(cudaMemset(e->kc, 0, kv_floats * 4)); CK(cudaMemset(e->vc, 0, kv_floats * 4));   // calloc'd in the reference (infer.c:47)
     CK(cudaMemset(e->x, 0, E * 4)); CK(cudaMemset(e->logits, 0, V * 4));
     const char *mega_env = getenv("NB200_MEGA");
-    MegaKern mk = (d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0)) ? nullptr : pick_mega(d);
+    // Default execution path, from the round-1 measurements on B200 (profiles/r1_paths.md): the cluster-resident kernel wins
+    // for small Q80 models, the CUDA-graph multi-kernel path for larger Q80 models, the persistent megakernel for F32/Q4K.
+    // NB200_MEGA=1 / NB200_CLUSTER=1 force a path, =0 forbids it.
+    const bool mega_forced = mega_env && atoi(mega_env) == 1;
+    const bool mega_default = (d.quant != 0x80u);
+    MegaKern mk = (d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0) || !(mega_default || mega_forced)) ? nullptr : pick_mega(d);
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) mk = nullptr;
@@ -858,7 +863,10 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     }
     {
         const char *cl_env = getenv("NB200_CLUSTER");
-        if (!(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0)) { if ((r = setup_cluster(e))) return r; }
+        const bool cl_forced = cl_env && atoi(cl_env) == 1;
+        const bool cl_default = e->weight_bytes < (256ull << 20);          // small models are latency-bound: keep activations on-chip
+        if (!(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0) && (cl_default || cl_forced)) { if ((r = setup_cluster(e))) return r; }
+        if (e->use_cluster) e->use_mega = false;
     }
     if (e->use_mega || e->use_cluster) {
         // nothing to capture: a token (or a whole run of tokens) is one launch
@@ -885,6 +893,7 @@ int nb200_get_config(const nb200_engine *e, nb200_config *c) {
     c->block_size = d.block_size; c->vocab_size = d.V; c->n_layer = d.L; c->n_embd = d.E; c->n_head = d.H;
     c->n_kv_head = d.KV; c->n_hidden = d.F; c->tied = (e->cls.w == e->emb.w); c->head_dim = d.hd;
     c->q_dim = d.q_dim; c->kv_dim = d.kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
+    c->reserved[0] = e->use_cluster ? 3u : e->use_mega ? 2u : (e->graph ? 1u : 0u);      // execution path: 3 cluster, 2 megakernel, 1 graph, 0 direct launches
     return 0;
 }
 

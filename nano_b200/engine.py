@@ -113,6 +113,9 @@ class Engine:
         for n, _t in Config._fields_[:-1]:
             setattr(self, n, int(getattr(cfg, n)))
         self.vocab = self.vocab_size
+        self.path = {3: "cluster-resident kernel (16-CTA cluster, DSMEM activations, TMA weight ring)",
+                     2: "persistent megakernel (cooperative launch, L2 grid barriers)",
+                     1: "multi-kernel CUDA graph with PDL", 0: "multi-kernel direct launches"}[int(cfg.reserved[0])]
 
     def close(self):
         if getattr(self, "h", None):

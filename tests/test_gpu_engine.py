@@ -66,7 +66,7 @@ def reference_noise_floor(name, quant, gs, path, S):
 
 @pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_CLUSTER, E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA], ids=["cluster", "megakernel", "multikernel"])
 @pytest.mark.parametrize("name,quant,gs", TOY)
-def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags):
+def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags, monkeypatch):
     """Fast mode (parallel fp32 reductions): within the north-star tolerance, or -- where the reference's own
     -O3 -ffast-math build already deviates more than that from its strict build on the same file (a 1-ulp
     upstream difference flips an int8/uint4 activation code) -- within 1.5x that measured noise floor.
@@ -74,6 +74,7 @@ def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags):
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S = 40
+    monkeypatch.setenv("NB200_CLUSTER", "1"); monkeypatch.setenv("NB200_MEGA", "1")     # force each path where the model supports it
     eng = E.Engine(path, S, flags=path_flags); o = ob.NanoOracle(path, S)
     toks = mf.teacher_tokens(S, spec.vocab)
     floor = reference_noise_floor(name, quant, gs, path, S)
@@ -145,9 +146,10 @@ def test_layer_level_with_injected_inputs(name, quant, gs):
 
 @pytest.mark.parametrize("penalty", [1.0, 1.3])
 @pytest.mark.parametrize("name,quant,gs", [("toy-qwen3", mf.QUANT_Q80, 64), ("toy-nano", mf.QUANT_F32, 128), ("mini-nano", mf.QUANT_Q4K, 128)])
-def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty):
+def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty, monkeypatch):
     """generate_next_token semantics (prefill forcing, penalty over ids[0..pos), first-max argmax): ids identical
     to the oracle in exact mode; the device-resident loop reproduces the per-call API loop."""
+    monkeypatch.setenv("NB200_CLUSTER", "1"); monkeypatch.setenv("NB200_MEGA", "1")
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S, P = 40, 6
