@@ -181,27 +181,39 @@ def cpu_baseline(workload, path, spec, seq, budget_s=25.0, quick=False):
 
 
 # --------------------------------------------------------------------------------------------------
-def dist_setup(n):
+def dist_setup(n, backend=None):
+    """One process per GPU (torchrun); NCCL when CUDA is present, gloo otherwise (CPU tests of the host logic)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
         return rank, world, local, dist
     return rank, world, local, None
 
 
 def barrier_max(dist, local, value):
-    """barrier + max over ranks of a float."""
+    """barrier + max over ranks of a float (the timing rule: a multi-GPU time is the max over ranks)."""
     if dist is None:
         return value
     import torch
-    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dev = f"cuda:{local}" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def aggregate_tokens_per_s(world, steps, tokens_per_step, ms_per_rank_max):
+    """Whole-job throughput of `world` independent batch-1 replicas: all ranks' tokens over the slowest rank's time."""
+    return world * steps * tokens_per_step / (ms_per_rank_max * 1e-3)
 
 
 def run_reference_arm(args, spec, quant, gs, seq, path):
@@ -284,7 +296,7 @@ def main():
     dec_ms = barrier_max(dist, local, dec_ms)
     wall = barrier_max(dist, local, wall)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * args.steps * n_dec / (dec_ms * 1e-3)
+    value = aggregate_tokens_per_s(world, args.steps, n_dec, dec_ms)
 
     # ---- e2e: per-token C-ABI calls with host buffers ----
     e2e_steps = max(1, min(args.steps, 2))
