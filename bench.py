@@ -245,7 +245,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="nano-168m-q80", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="replicas", choices=["replicas"])
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "tp"],
+                    help="replicas: one independent batch-1 session per GPU (weak scaling, the default the driver runs); "
+                         "tp: ONE session sharded over the GPUs through NVLink peer memory (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact", action="store_true", help="run the engine in exact (reference-order) mode")
     ap.add_argument("--no-pdl", action="store_true")
@@ -272,8 +274,18 @@ def main():
         dist.barrier()
     path = mf.cached_model(spec, quant, gs or 128)           # every rank finds the file rank 0 wrote
     flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_MEGA if args.no_mega else 0) | (E.FLAG_NO_CLUSTER if args.no_cluster else 0)
-    eng = E.Engine(path, seq, device=local, flags=flags)
+    tp = args.mode == "tp" and world > 1
+    if tp:
+        # one rank per process: exchange the CUDA IPC handles of the exchange blocks through torch.distributed
+        eng = E.Engine(path, seq, device=local, flags=flags, tp=(rank, world))
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.tp_export())
+        eng.tp_attach_ipc(handles)
+        dist.barrier()
+    else:
+        eng = E.Engine(path, seq, device=local, flags=flags)
     n_dec = seq - PROMPT
+    jobs = 1 if tp else world                                # sessions decoded concurrently
 
     # ---- warm-up (also brings clocks up) ----
     for _ in range(args.warmup):
@@ -296,7 +308,7 @@ def main():
     dec_ms = barrier_max(dist, local, dec_ms)
     wall = barrier_max(dist, local, wall)
     clocks = sampler.stop() if rank == 0 else None
-    value = aggregate_tokens_per_s(world, args.steps, n_dec, dec_ms)
+    value = aggregate_tokens_per_s(jobs, args.steps, n_dec, dec_ms)
 
     # ---- e2e: per-token C-ABI calls with host buffers ----
     e2e_steps = max(1, min(args.steps, 2))
@@ -310,9 +322,9 @@ def main():
             ids[pos + 1] = eng.next_greedy(ids, pos, 0)
         t_e2e += time.perf_counter() - t1
     t_e2e = barrier_max(dist, local, t_e2e)
-    e2e_value = world * e2e_steps * n_dec / t_e2e
+    e2e_value = jobs * e2e_steps * n_dec / t_e2e
 
-    if rank != 0:
+    if rank != 0 and not tp:
         eng.close()
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
@@ -326,16 +338,21 @@ def main():
     start = max(PROMPT, (seq // 2) - nprof // 2)
     eng.profile_tokens(ids, start, 4)                        # warm
     ms, cnt = eng.profile_tokens(ids, start, nprof)
+    if rank != 0:                                            # tensor-parallel ranks had to take part in the profiling pass
+        eng.close()
+        dist.barrier(); dist.destroy_process_group()
+        return
     E_, F_, Q_, K_ = spec.n_embd, spec.n_hidden, spec.q_dim, spec.kv_dim
     bpw = {mf.QUANT_F32: 4.0, mf.QUANT_Q80: 1.0 + 4.0 / max(gs, 1), mf.QUANT_Q4K: 148.0 / 256.0}[quant]
     mid = start + nprof / 2.0
+    T_ = world if tp else 1                                  # a tensor-parallel rank streams 1/T of every matrix and KV head
     alg = {   # algorithmic bytes per launch (weights once + gains + KV rows; activations not counted)
-        "qkv": (Q_ + 2 * K_) * E_ * bpw + 4 * E_ + 4 * K_,
-        "attention": 8 * K_ * (mid + 1) + (8 * spec.hd if spec.arch == mf.ARCH_QWEN3 else 0) + 4 * K_,
-        "o_proj": E_ * Q_ * bpw,
-        "w13_swiglu": 2 * F_ * E_ * bpw + 4 * E_,
-        "w2": E_ * F_ * bpw,
-        "classifier": spec.vocab * E_ * bpw + 4 * E_,
+        "qkv": (Q_ + 2 * K_) * E_ * bpw / T_ + 4 * E_ + 4 * K_ / T_,
+        "attention": (8 * K_ * (mid + 1) + 4 * K_) / T_ + (8 * spec.hd if spec.arch == mf.ARCH_QWEN3 else 0),
+        "o_proj": E_ * Q_ * bpw / T_,
+        "w13_swiglu": 2 * F_ * E_ * bpw / T_ + 4 * E_,
+        "w2": E_ * F_ * bpw / T_,
+        "classifier": spec.vocab * E_ * bpw / T_ + 4 * E_,
         "embed": 4 * E_,
     }
     per_class = {}
@@ -358,8 +375,21 @@ def main():
             "per_kernel": per_class}
     avg_pos = (PROMPT + seq - 1) / 2.0
     bytes_tok = spec.bytes_per_token(quant, gs, avg_pos)
-    token_roof = {"alg_bytes_per_token": bytes_tok, "achieved_gbs": bytes_tok * (value / world) / 1e9,
-                  "frac_of_peak": bytes_tok * (value / world) / 1e9 / peak, "roofline_tok_s": peak * 1e9 / bytes_tok}
+    per_gpu_gbs = bytes_tok * (value / world) / 1e9          # replicas: each GPU streams a whole model per token; tp: 1/T of it
+    token_roof = {"alg_bytes_per_token": bytes_tok, "achieved_gbs_per_gpu": per_gpu_gbs,
+                  "frac_of_peak": per_gpu_gbs / peak, "roofline_tok_s_per_session": peak * 1e9 / bytes_tok * (world if tp else 1)}
+    persistent = eng.path.startswith("cluster") or eng.path.startswith("persistent")
+    if persistent:
+        # the step IS one kernel: a launch decodes n_dec tokens, so the dominant kernel's roofline is the token roofline.
+        # per_kernel keeps the phase-by-phase profile of the same device code run as separate launches.
+        kname = "k_decode_cluster" if eng.path.startswith("cluster") else "k_decode_mega"
+        launch_us = dec_ms / args.steps * 1e3
+        roof = {"bound": "hbm", "kernel": f"{kname} (one launch decodes {n_dec} tokens: all layers + classifier + argmax)",
+                "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None,
+                "traffic_source": None, "peak_source": peak_src, "alg_bytes_per_launch": bytes_tok * n_dec,
+                "mean_launch_us": launch_us, "share_of_step": 1.0,
+                "phase_profile_note": "per_kernel = the same phase code launched as separate kernels (graph/PDL off), CUDA events per launch",
+                "per_kernel": per_class}
 
     cb = None
     if not args.no_cpu_baseline and world == 1:
@@ -367,11 +397,12 @@ def main():
 
     line = {
         "metric": "decode tokens/sec at batch=1", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if tp else "weak",
         "vs_baseline": None, "dtype": {mf.QUANT_Q80: "int8xint8->int32 + f32", mf.QUANT_Q4K: "u4xu4->int32 + f32", mf.QUANT_F32: "f32"}[quant],
         "data": "synthetic",
         "config": {"workload": f"{args.workload} greedy decode, seq={seq}, prompt={PROMPT}, max_seq_len={seq}",
-                   "parallelism": f"{world} independent batch-1 replica(s)", "mode": "exact" if args.exact else "fast",
+                   "parallelism": (f"tp{world}: one batch-1 session, row-sharded over {world} GPUs, activations exchanged through NVLink peer memory"
+                                   if tp else f"{world} independent batch-1 replica(s)"), "mode": "exact" if args.exact else "fast",
                    "engine": eng.path,
                    "l2": "inputs larger than L2: %.0f MB of weights (+KV) streamed per token vs 126 MB L2" % (eng.weight_bytes / 1e6),
                    "timing": "CUDA events around the decode segment of each step on the launching stream; max over ranks"},

@@ -85,6 +85,25 @@ int nb200_device_count(void);
 int nb200_engine_create(nb200_engine **out, const uint8_t *image, uint64_t image_bytes,
                         uint32_t max_seq_len, int device, uint32_t flags);
 void nb200_engine_destroy(nb200_engine *e);
+
+/* Tensor parallelism over NVLink peer memory (the reference has no counterpart, it is one CPU
+ * process).  Rank r of `tp_size` uploads its row slice of every matrix (whole kv-head groups for QKV and
+ * attention; contiguous row ranges for O, W1|W3, W2 and the classifier) and allocates an "exchange block"
+ * its peers write into.  After creation every rank must be attached to the others' blocks, either
+ *   - across processes: nb200_tp_export() -> 64-byte CUDA IPC handle; all-gather the handles with the
+ *     host's own transport (torch.distributed, MPI, a pipe); nb200_tp_attach_ipc(handles in rank order), or
+ *   - inside one process: nb200_tp_attach_local(array of the tp_size engines in rank order).
+ * From then on all ranks issue the SAME sequence of forward / next_greedy / decode_greedy calls with the
+ * same arguments (in lock-step; a rank that waits ~4 s for a missing peer fails with NB200_ECUDA).  Every
+ * rank returns the same token ids; nb200_read_logits fills only this rank's slice
+ * [rank*V/tp_size, (rank+1)*V/tp_size) of the vector.  Results are bit-identical to tp_size == 1.
+ * Fast mode only; needs n_kv_head, n_embd/2, n_hidden and vocab divisible by tp_size, head_dim <= 128. */
+int nb200_engine_create_tp(nb200_engine **out, const uint8_t *image, uint64_t image_bytes,
+                           uint32_t max_seq_len, int device, uint32_t flags, uint32_t tp_rank, uint32_t tp_size);
+int nb200_tp_export(nb200_engine *e, void *handle64);
+int nb200_tp_attach_ipc(nb200_engine *e, const void *handles /* tp_size x 64 bytes, rank order */);
+int nb200_tp_attach_local(nb200_engine *e, nb200_engine *const *group /* tp_size engines, rank order */);
+
 int nb200_get_config(const nb200_engine *e, nb200_config *cfg);
 
 /* one token through the network; logits stay in HBM.  is_causal=0 is the reference's seq2seq mode

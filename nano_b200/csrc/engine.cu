@@ -109,7 +109,15 @@ struct nb200_engine {
     std::vector<uint32_t> seen_mirror;   // ids whose seen[] flag is set, by position
     bool seen_valid = false;
     std::vector<void *> allocs;
+    // tensor parallel (kernels.cuh "Tensor parallelism"): exchange block = [TpHdr | x | xba | hb]; d holds the LOCAL head counts
     uint32_t tp_rank = 0, tp_size = 1;
+    bool tied = false;
+    uint32_t g_H = 0, g_KV = 0, g_q_dim = 0, g_kv_dim = 0;     // whole-model values (== d.* on one GPU)
+    unsigned char *tp_block = nullptr; size_t tp_block_bytes = 0;
+    uint32_t tp_off_x = 0, tp_off_xba = 0, tp_off_hb = 0;
+    unsigned char *tp_peer[kTpMax] = {};
+    std::vector<void *> tp_ipc_opened;
+    bool tp_attached = false;
     // per-kernel-class event profiling (nb200_profile_tokens)
     bool prof_on = false; int prof_tag = 0;
     struct ProfRec { int tag; cudaEvent_t a, b; };
@@ -155,24 +163,30 @@ int launch(nb200_engine *e, void (*kern)(const Args), dim3 grid, dim3 block, siz
 
 typedef void (*MatvecKern)(const MatvecArgs);
 
-template <int QUANT, int EPI>
+template <int QUANT, int EPI, bool TP>
 MatvecKern pick_matvec(int rb, int lpg) {
     if (QUANT == 0x80) {
-#define NB_PICK(RB_, L_) if (rb == RB_ && lpg == L_) return k_matvec<QUANT, EPI, RB_, L_>;
+#define NB_PICK(RB_, L_) if (rb == RB_ && lpg == L_) return k_matvec<QUANT, EPI, RB_, L_, TP>;
         NB_PICK(2, 2) NB_PICK(2, 4) NB_PICK(2, 8) NB_PICK(2, 16)
         NB_PICK(4, 2) NB_PICK(4, 4) NB_PICK(4, 8) NB_PICK(4, 16)
 #undef NB_PICK
         return nullptr;
     }
-    if (rb == 2) return k_matvec<QUANT, EPI, 2, 8>;
-    return k_matvec<QUANT, EPI, 4, 8>;
+    if (rb == 2) return k_matvec<QUANT, EPI, 2, 8, TP>;
+    return k_matvec<QUANT, EPI, 4, 8, TP>;
 }
 
 template <int EPI>
-MatvecKern pick_matvec_q(uint32_t quant, int rb, int lpg) {
-    if (quant == 0x00u) return pick_matvec<0x00, EPI>(rb, lpg);
-    if (quant == 0x80u) return pick_matvec<0x80, EPI>(rb, lpg);
-    return pick_matvec<0x42, EPI>(rb, lpg);
+MatvecKern pick_matvec_q(uint32_t quant, int rb, int lpg, bool tp) {
+    if (tp && EPI != EPI_STORE) {      // the tensor-parallel variants (STORE is an op-level kernel only)
+        constexpr int E2 = (EPI == EPI_STORE) ? EPI_RESID : EPI;
+        if (quant == 0x00u) return pick_matvec<0x00, E2, true>(rb, lpg);
+        if (quant == 0x80u) return pick_matvec<0x80, E2, true>(rb, lpg);
+        return pick_matvec<0x42, E2, true>(rb, lpg);
+    }
+    if (quant == 0x00u) return pick_matvec<0x00, EPI, false>(rb, lpg);
+    if (quant == 0x80u) return pick_matvec<0x80, EPI, false>(rb, lpg);
+    return pick_matvec<0x42, EPI, false>(rb, lpg);
 }
 
 int grid_mult() {
@@ -206,12 +220,13 @@ int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, 
     int rb = (m.rows >= total_warps * 8) ? 4 : 2;
     const int lpg = (d.quant == 0x80u) ? (int)(d.gs / 16) : 8;
     MatvecKern k = nullptr;
+    const bool tp = a.tp.size > 1;
     switch (epi) {
-        case EPI_STORE: k = pick_matvec_q<EPI_STORE>(d.quant, rb, lpg); break;
-        case EPI_QKV: k = pick_matvec_q<EPI_QKV>(d.quant, rb, lpg); break;
-        case EPI_RESID: k = pick_matvec_q<EPI_RESID>(d.quant, rb, lpg); break;
-        case EPI_SWIGLU: k = pick_matvec_q<EPI_SWIGLU>(d.quant, rb, lpg); break;
-        case EPI_CLS: k = pick_matvec_q<EPI_CLS>(d.quant, rb, lpg); break;
+        case EPI_STORE: k = pick_matvec_q<EPI_STORE>(d.quant, rb, lpg, tp); break;
+        case EPI_QKV: k = pick_matvec_q<EPI_QKV>(d.quant, rb, lpg, tp); break;
+        case EPI_RESID: k = pick_matvec_q<EPI_RESID>(d.quant, rb, lpg, tp); break;
+        case EPI_SWIGLU: k = pick_matvec_q<EPI_SWIGLU>(d.quant, rb, lpg, tp); break;
+        case EPI_CLS: k = pick_matvec_q<EPI_CLS>(d.quant, rb, lpg, tp); break;
     }
     if (!k) return fail(NB200_EINVAL, "no matvec kernel for quant=0x%x gs=%u", d.quant, d.gs);
     const uint32_t nblocks = (m.rows + rb - 1) / rb;
@@ -219,6 +234,7 @@ int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, 
     const uint32_t cap = (uint32_t)num_sms * grid_mult();
     if (grid > cap) grid = cap;
     if (epi == EPI_CLS && e) { if (grid > e->cls_grid) grid = e->cls_grid; }
+    a.tp.expected = grid;
     return launch<MatvecArgs>(e, k, dim3(grid), dim3(kThreads), smem, a);
 }
 
@@ -226,6 +242,17 @@ MatvecArgs base_args(nb200_engine *e) {
     MatvecArgs a{};
     a.d = e->d; a.st = e->st;
     return a;
+}
+
+// Exchange ids within one token: layer l publishes attention = 4l+1, O = 4l+2, W1|W3 = 4l+3, W2 = 4l+4; the classifier's
+// argmax all-gather is 4L+1.  Each kernel waits for the exchange that produced its input vector.
+TpArgs tp_args(nb200_engine *e, uint32_t wait_ph, uint32_t signal_ph, uint32_t row_base, uint32_t out_off) {
+    TpArgs t{};
+    if (e->tp_size <= 1) return t;
+    t.size = e->tp_size; t.rank = e->tp_rank; t.wait_ph = wait_ph; t.signal_ph = signal_ph; t.nph = 4 * e->d.L + 1;
+    t.row_base = row_base; t.out_off = out_off; t.expected = 1;
+    for (uint32_t p = 0; p < e->tp_size; p++) t.peer[p] = e->tp_peer[p];
+    return t;
 }
 
 int run_embed(nb200_engine *e) {
@@ -244,6 +271,7 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.src = e->x; a.gain = e->norm_attn + (size_t)l * d.E;
         a.out = e->q; a.out_k = e->kraw; a.out_v = e->vc + l * kvl;
         a.dump_codes = e->dump_codes; a.dump_scales = e->dump_scales;
+        a.tp = tp_args(e, 4 * l, 0, 0, 0);
         e->prof_tag = 1;
         if ((r = run_matvec(e, EPI_QKV, e->qkv[l], a, true, e->num_sms))) return r;
     }
@@ -258,12 +286,14 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.st = e->st; a.nsplit_max = e->nsplit_max; a.chunk_cap = e->chunk_cap; a.d = d;
         void (*kern)(const AttnArgs) = k_attention;
         uint32_t smem = e->attn_smem;
-        if (d.hd <= 128 && (d.arch != 3u || (d.hd & (d.hd - 1)) == 0) && !getenv("NB200_GENERIC_ATTN")) {
+        const bool tp = e->tp_size > 1;
+        if (tp) { a.tp = tp_args(e, 0, 4 * l + 1, e->tp_rank * d.q_dim, e->tp_off_xba); a.tp.expected = d.KV; }
+        if (d.hd <= 128 && (d.arch != 3u || (d.hd & (d.hd - 1)) == 0) && (tp || !getenv("NB200_GENERIC_ATTN"))) {
             switch (d.kv_mul) {
-                case 1: kern = k_attention_fast<1>; break;
-                case 2: kern = k_attention_fast<2>; break;
-                case 4: kern = k_attention_fast<4>; break;
-                case 8: kern = k_attention_fast<8>; break;
+                case 1: kern = tp ? k_attention_fast<1, true> : k_attention_fast<1>; break;
+                case 2: kern = tp ? k_attention_fast<2, true> : k_attention_fast<2>; break;
+                case 4: kern = tp ? k_attention_fast<4, true> : k_attention_fast<4>; break;
+                case 8: kern = tp ? k_attention_fast<8, true> : k_attention_fast<8>; break;
                 default: break;
             }
             if (kern != k_attention) smem = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kWarps) * 4u;
@@ -280,18 +310,21 @@ int run_layer(nb200_engine *e, uint32_t l) {
     {   // F3: quantise(xba) + O matvec + residual
         MatvecArgs a = base_args(e);
         a.src = e->xba; a.gain = nullptr; a.out = e->x;
+        a.tp = tp_args(e, 4 * l + 1, 4 * l + 2, e->tp_rank * e->wo[l].rows, e->tp_off_x);
         e->prof_tag = 3;
         if ((r = run_matvec(e, EPI_RESID, e->wo[l], a, false, e->num_sms))) return r;
     }
     {   // F4: rmsnorm + quantise + W1|W3 matvec + SwiGLU
         MatvecArgs a = base_args(e);
         a.src = e->x; a.gain = e->norm_ffn + (size_t)l * d.E; a.out = e->hb;
+        a.tp = tp_args(e, 4 * l + 2, 4 * l + 3, e->tp_rank * (e->w13[l].rows / 2), e->tp_off_hb);
         e->prof_tag = 4;
         if ((r = run_matvec(e, EPI_SWIGLU, e->w13[l], a, true, e->num_sms))) return r;
     }
     {   // F5: quantise(hb) + W2 matvec + residual
         MatvecArgs a = base_args(e);
         a.src = e->hb; a.gain = nullptr; a.out = e->x;
+        a.tp = tp_args(e, 4 * l + 3, 4 * l + 4, e->tp_rank * e->w2[l].rows, e->tp_off_x);
         e->prof_tag = 5;
         if ((r = run_matvec(e, EPI_RESID, e->w2[l], a, false, e->num_sms))) return r;
     }
@@ -309,6 +342,7 @@ int run_classifier(nb200_engine *e) {
         return launch<FinalizeArgs>(e, k_cls_finalize, dim3(1), dim3(1024), 0, f);
     }
     a.st_rw = e->st; a.seen = e->seen; a.seen_rw = e->seen; a.cls_val = e->cls_val; a.cls_idx = e->cls_idx; a.ids = e->ids_dev;
+    a.tp = tp_args(e, 4 * e->d.L, 4 * e->d.L + 1, e->tp_rank * e->cls.rows, 0);
     return run_matvec(e, EPI_CLS, e->cls, a, true, e->num_sms);
 }
 
@@ -378,6 +412,7 @@ int launch_cluster(nb200_engine *e, uint32_t n_steps) {
 }
 
 int launch_token(nb200_engine *e) {
+    if (e->tp_size > 1 && !e->tp_attached) return fail(NB200_EINVAL, "tensor-parallel engine: attach the peer ranks first (nb200_tp_attach_*)");
     if (e->use_cluster) return launch_cluster(e, 1);
     if (e->use_mega) return launch_mega(e, 1);
     if (e->graph) {
@@ -617,6 +652,7 @@ void nb200_engine_destroy(nb200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->graph) cudaGraphExecDestroy(e->graph);
+    for (void *p : e->tp_ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : e->allocs) cudaFree(p);
     if (e->st_host) cudaFreeHost(e->st_host);
     if (e->tok_host) cudaFreeHost(e->tok_host);
@@ -624,9 +660,12 @@ void nb200_engine_destroy(nb200_engine *e) {
     delete e;
 }
 
-int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
-                        uint32_t flags) {
+static int finish_paths(nb200_engine *e);
+
+static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
+                       uint32_t flags, uint32_t tp_rank, uint32_t tp_size) {
     if (!out || !img || image_bytes < 260 || max_seq_len == 0) return fail(NB200_EINVAL, "bad arguments");
+    if (tp_size < 1 || tp_size > (uint32_t)kTpMax || tp_rank >= tp_size) return fail(NB200_EINVAL, "bad tensor-parallel rank/size");
     *out = nullptr;
     if (nb200_device_count() <= 0) return fail(NB200_ENODEV, "no CUDA device: nano_b200 has no CPU path");
     if (rd_u32(img) != 0x42443453u || rd_u32(img + 4) != 0x55524c4du) return fail(NB200_EINVAL, "bad magic (not a BD4SURLM file)");
@@ -637,7 +676,7 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     }
     nb200_engine *e = new nb200_engine();
     struct Guard { nb200_engine *e; bool ok = false; ~Guard() { if (!ok) nb200_engine_destroy(e); } } guard{e};
-    e->device = device; e->flags = flags;
+    e->device = device; e->flags = flags; e->tp_rank = tp_rank; e->tp_size = tp_size;
     e->use_pdl = !(flags & NB200_FLAG_NO_PDL);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -671,6 +710,14 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     if (d.quant == 0x42u && (d.E % 256 || d.q_dim % 256 || d.F % 256))
         return fail(NB200_EINVAL, "Q4K needs n %% 256 == 0 (the reference's partial-block offset is wrong otherwise, tensor.c:307)");
     if (d.quant != 0x80u) d.gs = (d.quant == 0x42u) ? 32 : 1;
+    e->g_H = d.H; e->g_KV = d.KV; e->g_q_dim = d.q_dim; e->g_kv_dim = d.kv_dim;
+    const uint32_t T = tp_size;
+    if (T > 1) {
+        // row shards: whole kv-head groups for QKV/attention, contiguous row ranges for O / W1|W3 / W2 / classifier
+        if (d.exact) return fail(NB200_EINVAL, "tensor parallel runs in fast mode only");
+        if (d.KV % T || d.E % (2 * T) || d.F % T || d.V % T) return fail(NB200_EINVAL, "tensor parallel size %u does not divide kv heads / n_embd / n_hidden / vocab", T);
+        if (d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0)) return fail(NB200_EINVAL, "tensor parallel needs head_dim <= 128 (power of two for Qwen3)");
+    }
 
     // ---- parameter map (infer.c:100-217) ----
     const uint32_t tok_bytes = rd_u32(img + 256);
@@ -769,32 +816,63 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     }
     struct StagingFree { uint8_t *p; ~StagingFree() { if (p) cudaFree(p); } } sfree{staging};
     int r;
+    // source rows [row0, ...) of an [rows x n] tensor in the file's own layout
+    auto srcw = [&](const uint8_t *w, uint64_t row0, uint64_t n) -> const uint8_t * {
+        return w + (d.quant == 0x00u ? row0 * n * 4 : d.quant == 0x80u ? row0 * n : row0 * (n / 256) * 160);
+    };
+    auto srca = [&](const uint8_t *a, uint64_t row0, uint64_t n) -> const uint8_t * { return a ? a + row0 * (n / d.gs) * 4 : nullptr; };
+    const uint64_t QDl = QD / T, KDl = KD / T, El = E / T, Fl = F / T, Vl = V / T, rk = tp_rank;
     e->qkv.resize(L); e->wo.resize(L); e->w13.resize(L); e->w2.resize(L);
     for (uint64_t l = 0; l < L; l++) {
-        if ((r = alloc_mat(e, e->qkv[l], (uint32_t)(QD + 2 * KD), (uint32_t)E))) return r;
-        if ((r = put_rows(e, e->qkv[l], src_w[0][l], src_a[0][l], (uint32_t)QD, 0, 1, staging))) return r;
-        if ((r = put_rows(e, e->qkv[l], src_w[1][l], src_a[1][l], (uint32_t)KD, (uint32_t)QD, 1, staging))) return r;
-        if ((r = put_rows(e, e->qkv[l], src_w[2][l], src_a[2][l], (uint32_t)KD, (uint32_t)(QD + KD), 1, staging))) return r;
-        if ((r = alloc_mat(e, e->wo[l], (uint32_t)E, (uint32_t)QD))) return r;
-        if ((r = put_rows(e, e->wo[l], src_w[3][l], src_a[3][l], (uint32_t)E, 0, 1, staging))) return r;
-        if ((r = alloc_mat(e, e->w13[l], (uint32_t)(2 * F), (uint32_t)E))) return r;
-        if ((r = put_rows(e, e->w13[l], src_w[4][l], src_a[4][l], (uint32_t)F, 0, 2, staging))) return r;
-        if ((r = put_rows(e, e->w13[l], src_w[6][l], src_a[6][l], (uint32_t)F, 1, 2, staging))) return r;
-        if ((r = alloc_mat(e, e->w2[l], (uint32_t)E, (uint32_t)F))) return r;
-        if ((r = put_rows(e, e->w2[l], src_w[5][l], src_a[5][l], (uint32_t)E, 0, 1, staging))) return r;
+        if ((r = alloc_mat(e, e->qkv[l], (uint32_t)(QDl + 2 * KDl), (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->qkv[l], srcw(src_w[0][l], rk * QDl, E), srca(src_a[0][l], rk * QDl, E), (uint32_t)QDl, 0, 1, staging))) return r;
+        if ((r = put_rows(e, e->qkv[l], srcw(src_w[1][l], rk * KDl, E), srca(src_a[1][l], rk * KDl, E), (uint32_t)KDl, (uint32_t)QDl, 1, staging))) return r;
+        if ((r = put_rows(e, e->qkv[l], srcw(src_w[2][l], rk * KDl, E), srca(src_a[2][l], rk * KDl, E), (uint32_t)KDl, (uint32_t)(QDl + KDl), 1, staging))) return r;
+        if ((r = alloc_mat(e, e->wo[l], (uint32_t)El, (uint32_t)QD))) return r;
+        if ((r = put_rows(e, e->wo[l], srcw(src_w[3][l], rk * El, QD), srca(src_a[3][l], rk * El, QD), (uint32_t)El, 0, 1, staging))) return r;
+        if ((r = alloc_mat(e, e->w13[l], (uint32_t)(2 * Fl), (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->w13[l], srcw(src_w[4][l], rk * Fl, E), srca(src_a[4][l], rk * Fl, E), (uint32_t)Fl, 0, 2, staging))) return r;
+        if ((r = put_rows(e, e->w13[l], srcw(src_w[6][l], rk * Fl, E), srca(src_a[6][l], rk * Fl, E), (uint32_t)Fl, 1, 2, staging))) return r;
+        if ((r = alloc_mat(e, e->w2[l], (uint32_t)El, (uint32_t)F))) return r;
+        if ((r = put_rows(e, e->w2[l], srcw(src_w[5][l], rk * El, F), srca(src_a[5][l], rk * El, F), (uint32_t)El, 0, 1, staging))) return r;
     }
+    // every rank keeps the whole embedding table (one row is read per token); the classifier reads its V/T row slice
+    const uint64_t wb_before_emb = e->weight_bytes;
     if ((r = alloc_mat(e, e->emb, (uint32_t)V, (uint32_t)E))) return r;
     if ((r = put_rows(e, e->emb, emb_w, emb_a, (uint32_t)V, 0, 1, staging))) return r;
     if (cls_w) {
-        if ((r = alloc_mat(e, e->cls, (uint32_t)V, (uint32_t)E))) return r;
-        if ((r = put_rows(e, e->cls, cls_w, cls_a, (uint32_t)V, 0, 1, staging))) return r;
+        e->weight_bytes = wb_before_emb;
+        if ((r = alloc_mat(e, e->cls, (uint32_t)Vl, (uint32_t)E))) return r;
+        if ((r = put_rows(e, e->cls, srcw(cls_w, rk * Vl, E), srca(cls_a, rk * Vl, E), (uint32_t)Vl, 0, 1, staging))) return r;
     } else {
-        e->cls = e->emb;
+        e->cls = e->emb; e->tied = true;
+        if (T > 1) {
+            e->weight_bytes = wb_before_emb + (e->weight_bytes - wb_before_emb) / T;
+            e->cls.rows = (uint32_t)Vl;
+            const uint64_t row0 = rk * Vl;
+            if (d.quant == 0x00u) e->cls.w = (uint8_t *)e->emb.w + row0 * E * 4;
+            else if (d.quant == 0x80u) { e->cls.w = (uint8_t *)e->emb.w + row0 * E; e->cls.aux = (uint8_t *)e->emb.aux + row0 * (E / d.gs) * 4; }
+            else { e->cls.w = (uint8_t *)e->emb.w + row0 * E / 2; e->cls.aux = (uint8_t *)e->emb.aux + row0 * (E / 256) * 20; }
+        }
     }
+    // from here on d carries the LOCAL head counts (attention and the QKV epilogue index local heads)
+    d.H /= T; d.KV /= T; d.q_dim = (uint32_t)QDl; d.kv_dim = (uint32_t)KDl;
 
     // ---- activations, KV cache, workspaces ----
     const size_t kv_floats = (size_t)L * d.KV * d.max_seq * d.hd;
-    DM(e->x, E * 4); DM(e->q, QD * 4); DM(e->kraw, KD * 4); DM(e->xba, QD * 4); DM(e->hb, F * 4); DM(e->logits, V * 4);
+    if (T > 1) {
+        // exchange block: the three replicated activation vectors live where the peers can write them
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        e->tp_off_x = kTpHdrBytes; e->tp_off_xba = (uint32_t)(e->tp_off_x + al(E * 4)); e->tp_off_hb = (uint32_t)(e->tp_off_xba + al(QD * 4));
+        e->tp_block_bytes = e->tp_off_hb + al(F * 4);
+        DM(e->tp_block, e->tp_block_bytes);
+        CK(cudaMemset(e->tp_block, 0, e->tp_block_bytes));
+        e->x = (float *)(e->tp_block + e->tp_off_x); e->xba = (float *)(e->tp_block + e->tp_off_xba); e->hb = (float *)(e->tp_block + e->tp_off_hb);
+        e->tp_peer[tp_rank] = e->tp_block;
+    } else {
+        DM(e->x, E * 4); DM(e->xba, QD * 4); DM(e->hb, F * 4);
+    }
+    DM(e->q, QD * 4); DM(e->kraw, KD * 4); DM(e->logits, V * 4);
     DM(e->kc, kv_floats * 4); DM(e->vc, kv_floats * 4);
     CK(cudaMemset(e->kc, 0, kv_floats * 4)); CK(cudaMemset(e->vc, 0, kv_floats * 4));   // calloc'd in the reference (infer.c:47)
     CK(cudaMemset(e->x, 0, E * 4)); CK(cudaMemset(e->logits, 0, V * 4));
@@ -804,11 +882,11 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
     // NB200_MEGA=1 / NB200_CLUSTER=1 force a path, =0 forbids it.
     const bool mega_forced = mega_env && atoi(mega_env) == 1;
     const bool mega_default = (d.quant != 0x80u);
-    MegaKern mk = (d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0) || !(mega_default || mega_forced)) ? nullptr : pick_mega(d);
+    MegaKern mk = (T > 1 || d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0) || !(mega_default || mega_forced)) ? nullptr : pick_mega(d);
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) mk = nullptr;
-    uint32_t nsm = (uint32_t)e->num_sms / d.KV;     // (kv head, split) items <= one per SM; same split in both paths => identical bits
+    uint32_t nsm = (uint32_t)e->num_sms / e->g_KV;  // (kv head, split) items <= one per SM; same split in every path and TP size => identical bits
     if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
     e->nsplit_max = nsm;
     uint32_t cap = (d.max_seq + nsm - 1) / nsm; cap = (cap + 7u) & ~7u; if (cap < 32) cap = 32;
@@ -865,12 +943,20 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
         const char *cl_env = getenv("NB200_CLUSTER");
         const bool cl_forced = cl_env && atoi(cl_env) == 1;
         const bool cl_default = e->weight_bytes < (256ull << 20);          // small models are latency-bound: keep activations on-chip
-        if (!(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0) && (cl_default || cl_forced)) { if ((r = setup_cluster(e))) return r; }
+        if (T == 1 && !(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0) && (cl_default || cl_forced)) { if ((r = setup_cluster(e))) return r; }
         if (e->use_cluster) e->use_mega = false;
     }
+    if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
+    guard.ok = true;
+    *out = e;
+    return 0;
+}
+
+static int finish_paths(nb200_engine *e) {
+    int r = 0;
     if (e->use_mega || e->use_cluster) {
         // nothing to capture: a token (or a whole run of tokens) is one launch
-    } else if (!(flags & NB200_FLAG_NO_GRAPH)) {
+    } else if (!(e->flags & NB200_FLAG_NO_GRAPH)) {
         r = capture_graph(e);
         if (r && e->use_pdl) {          // retry without PDL edges before giving up on the graph
             e->use_pdl = false;
@@ -878,11 +964,72 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
         }
         if (r) return r;
     } else {
-        e->launches_per_token = 2 + 5 * d.L;
+        e->launches_per_token = 2 + 5 * e->d.L;
     }
-    guard.ok = true;
-    *out = e;
     return 0;
+}
+
+int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
+                        uint32_t flags) {
+    return create_impl(out, img, image_bytes, max_seq_len, device, flags, 0, 1);
+}
+
+int nb200_engine_create_tp(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
+                           uint32_t flags, uint32_t tp_rank, uint32_t tp_size) {
+    return create_impl(out, img, image_bytes, max_seq_len, device, flags, tp_rank, tp_size);
+}
+
+int nb200_tp_export(nb200_engine *e, void *handle64) {
+    if (!e || !handle64 || e->tp_size <= 1) return fail(NB200_EINVAL, "not a tensor-parallel engine");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->tp_block));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+static int tp_finish_attach(nb200_engine *e) {
+    e->tp_attached = true;
+    return finish_paths(e);
+}
+
+int nb200_tp_attach_ipc(nb200_engine *e, const void *handles) {
+    if (!e || !handles || e->tp_size <= 1) return fail(NB200_EINVAL, "not a tensor-parallel engine");
+    if (e->tp_attached) return fail(NB200_EINVAL, "already attached");
+    CK(cudaSetDevice(e->device));
+    for (uint32_t p = 0; p < e->tp_size; p++) {
+        if (p == e->tp_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) return fail(NB200_ECUDA, "cudaIpcOpenMemHandle(rank %u) failed: %s", p, cudaGetErrorString(ce));
+        e->tp_ipc_opened.push_back(ptr);
+        e->tp_peer[p] = (unsigned char *)ptr;
+    }
+    return tp_finish_attach(e);
+}
+
+int nb200_tp_attach_local(nb200_engine *e, nb200_engine *const *group) {
+    if (!e || !group || e->tp_size <= 1) return fail(NB200_EINVAL, "not a tensor-parallel engine");
+    if (e->tp_attached) return fail(NB200_EINVAL, "already attached");
+    CK(cudaSetDevice(e->device));
+    for (uint32_t p = 0; p < e->tp_size; p++) {
+        nb200_engine *g = group[p];
+        if (!g || g->tp_size != e->tp_size || g->tp_rank != p || g->tp_block_bytes != e->tp_block_bytes) return fail(NB200_EINVAL, "group[%u] is not rank %u of this group", p, p);
+        if (p == e->tp_rank) continue;
+        if (g->device != e->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, e->device, g->device));
+            if (!can) return fail(NB200_ECUDA, "device %d cannot access device %d", e->device, g->device);
+            cudaError_t ce = cudaDeviceEnablePeerAccess(g->device, 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(NB200_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(ce));
+            cudaGetLastError();
+        }
+        e->tp_peer[p] = g->tp_block;
+    }
+    return tp_finish_attach(e);
 }
 
 int nb200_get_config(const nb200_engine *e, nb200_config *c) {
@@ -890,10 +1037,19 @@ int nb200_get_config(const nb200_engine *e, nb200_config *c) {
     memset(c, 0, sizeof *c);
     const Dims &d = e->d;
     c->arch = d.arch; c->quant = d.quant; c->group_size = (d.quant == 0x80u) ? d.gs : 0;
-    c->block_size = d.block_size; c->vocab_size = d.V; c->n_layer = d.L; c->n_embd = d.E; c->n_head = d.H;
-    c->n_kv_head = d.KV; c->n_hidden = d.F; c->tied = (e->cls.w == e->emb.w); c->head_dim = d.hd;
-    c->q_dim = d.q_dim; c->kv_dim = d.kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
+    c->block_size = d.block_size; c->vocab_size = d.V; c->n_layer = d.L; c->n_embd = d.E;
+    c->n_head = e->g_H; c->n_kv_head = e->g_KV; c->n_hidden = d.F; c->tied = e->tied ? 1u : 0u; c->head_dim = d.hd;
+    c->q_dim = e->g_q_dim; c->kv_dim = e->g_kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
     c->reserved[0] = e->use_cluster ? 3u : e->use_mega ? 2u : (e->graph ? 1u : 0u);      // execution path: 3 cluster, 2 megakernel, 1 graph, 0 direct launches
+    return 0;
+}
+
+// after a stream sync: did a tensor-parallel spin give up on a peer?
+static int tp_check(nb200_engine *e) {
+    if (e->tp_size <= 1) return 0;
+    uint32_t t = 0;
+    CK(cudaMemcpy(&t, e->tp_block + offsetof(TpHdr, timeout), 4, cudaMemcpyDeviceToHost));
+    if (t) return fail(NB200_ECUDA, "tensor parallel: rank %u timed out waiting for a peer (ranks must issue the same calls)", e->tp_rank);
     return 0;
 }
 
@@ -916,7 +1072,7 @@ int nb200_forward(nb200_engine *e, uint32_t token, uint32_t pos, uint32_t is_cau
     if ((r = push_state(e, pos, is_causal ? 1u : 0u, 0, 0, 1.0f, token, 1))) return r;
     if ((r = launch_token(e))) return r;
     CK(cudaStreamSynchronize(e->stream));
-    return 0;
+    return tp_check(e);
 }
 
 int nb200_read_logits(nb200_engine *e, float *host_logits) {
@@ -956,7 +1112,7 @@ int nb200_next_greedy(nb200_engine *e, const uint32_t *ids, uint32_t pos, int is
     CK(cudaMemcpyAsync(e->tok_host, &e->st->next_token, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     *next = is_prefilling ? ids[pos + 1] : *e->tok_host;
-    return 0;
+    return tp_check(e);
 }
 
 int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint32_t n_total, float penalty,
@@ -989,7 +1145,7 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     if (prefill_ms) *prefill_ms = a;
     if (device_ms) *device_ms = b;
     for (auto &v : ev) cudaEventDestroy(v);
-    return 0;
+    return tp_check(e);
 }
 
 int nb200_read_buffer(nb200_engine *e, int field, uint32_t layer, uint32_t pos, float *dst, uint32_t count) {

@@ -51,6 +51,74 @@ struct DevState {
     uint32_t pad[3];
 };
 
+// ------------------------------------------------------------------------------------------------
+// Tensor parallelism over NVLink peer memory (there is no reference code for this, the reference is one CPU).
+// Every rank owns a row slice of each matrix (whole kv-head groups for QKV/attention) and keeps the FULL activation
+// vectors x / xba / hb in an "exchange block" that its peers can write.  A producing kernel's epilogue pushes each
+// finished element into every peer's copy (plain st.global over NVLink, no remote reads anywhere), then the last CTA
+// publishes an epoch number into every peer's flag word; the consuming kernel spins on its LOCAL flag words.  Row dots
+// are computed exactly as on one GPU and every rank quantises the same full vector, so results are bit-identical to
+// the single-GPU engine.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTpMax = 8;
+struct TpHdr {                     // first 256 bytes of the exchange block
+    uint32_t flags[kTpMax];        // flags[r]: last epoch rank r published to me
+    uint32_t epoch_base;           // phases completed by earlier tokens (local; bumped by the classifier's last CTA)
+    uint32_t ticket[2];            // last-CTA election of the publishing kernel (local)
+    uint32_t timeout;              // set when a spin gave up (peer died): results are garbage, host reports an error
+    float cls_v[kTpMax];           // per-rank argmax partials (written by peers)
+    uint32_t cls_i[kTpMax];
+};
+constexpr uint32_t kTpHdrBytes = 256;
+struct TpArgs {
+    uint32_t size, rank;           // size <= 1: single GPU, everything below ignored
+    uint32_t wait_ph, signal_ph;   // 1-based exchange ids within a token (0 = none); epoch = epoch_base + id
+    uint32_t nph;                  // exchanges per token
+    uint32_t row_base;             // global index of local output row 0
+    uint32_t out_off;              // byte offset of the output vector inside the exchange block
+    uint32_t expected;             // CTAs that take part in the publishing election
+    unsigned char *peer[kTpMax];   // exchange block of every rank (peer[rank] = own)
+};
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ TpHdr *tp_hdr(const TpArgs &tp, uint32_t r) { return reinterpret_cast<TpHdr *>(tp.peer[r]); }
+// spin until rank r's flag in MY block reaches `need`; gives up after ~4 s so a dead peer cannot hang the GPU
+__device__ __forceinline__ void tp_spin(const TpArgs &tp, uint32_t r, uint32_t need) {
+    TpHdr *h = tp_hdr(tp, tp.rank);
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(&h->flags[r]) - need) < 0) {
+        if (clock64() - t0 > 8000000000ll) { h->timeout = 1; break; }
+    }
+}
+// consumer side: threads 0..size-1 each wait for one producer rank; the CTA continues after the barrier
+__device__ __forceinline__ void tp_wait(const TpArgs &tp) {
+    if (tp.wait_ph && threadIdx.x < tp.size) tp_spin(tp, threadIdx.x, __ldcg(&tp_hdr(tp, tp.rank)->epoch_base) + tp.wait_ph);
+    __syncthreads();
+}
+// push one finished element into every rank's copy of the output vector
+__device__ __forceinline__ void tp_store(const TpArgs &tp, uint32_t idx, float v) {
+    for (uint32_t p = 0; p < tp.size; p++) reinterpret_cast<float *>(tp.peer[p] + tp.out_off)[idx] = v;
+}
+// producer side, end of kernel.  Precondition: every thread that called tp_store has executed __threadfence_system()
+// and the CTA has synchronised.  The last of `expected` CTAs publishes the epoch to every rank.
+__device__ __forceinline__ void tp_publish(const TpArgs &tp, uint32_t slot) {
+    if (threadIdx.x == 0) {
+        TpHdr *h = tp_hdr(tp, tp.rank);
+        __threadfence();
+        const uint32_t t = atomicAdd(&h->ticket[slot], 1u);
+        if (t == tp.expected - 1) {
+            h->ticket[slot] = 0;
+            __threadfence_system();
+            const uint32_t epoch = __ldcg(&h->epoch_base) + tp.signal_ph;
+            for (uint32_t p = 0; p < tp.size; p++) st_release_sys(&tp_hdr(tp, p)->flags[tp.rank], epoch);
+        }
+    }
+}
+
 enum Epilogue { EPI_STORE = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_CLS = 4 };
 
 struct MatvecArgs {
@@ -77,6 +145,7 @@ struct MatvecArgs {
     uint32_t state_known, pos_val; float pen_val;
     unsigned long long *dbg;     // optional: CTA 0 / thread 0 clock64() stamps inside the phase (tools/gpu_trace.py)
     Dims d;
+    TpArgs tp;                   // tensor-parallel exchange (k_matvec<..., TP=true> only)
 };
 #define NB_STAMP(ptr, k) do { if ((ptr) && blockIdx.x == 0 && threadIdx.x == 0) (ptr)[k] = clock64(); } while (0)
 
@@ -537,9 +606,11 @@ __device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows
     if (gain && warp == 0) for (uint32_t off = (cta * 32u + lane) * 32u; off < n; off += ncta * 32u * 32u) prefetch_l2(gain + off);
 }
 
-template <int QUANT, int EPI, int RB, int LPG>
+template <int QUANT, int EPI, int RB, int LPG, bool TP = false>
 __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, uint32_t ncta, unsigned char *act, MatvecSmem &ms) {
     const Dims &d = a.d;
+    // tensor parallel: local row r is element rbase + r of the (replicated) output vector; QKV outputs stay local
+    const uint32_t rbase = (TP && EPI != EPI_QKV) ? a.tp.row_base : 0u;
     const bool exact = d.exact != 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblocks = (a.rows + RB - 1) / RB;
@@ -555,7 +626,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
         q80_load<RB, LPG>(pre, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), gwarp * RB, a.rows, a.n, 0);
     if (EPI == EPI_RESID && has_first) {
 #pragma unroll
-        for (int r = 0; r < RB; r++) xres[r] = __ldcg(a.out + min(gwarp * RB + r, a.rows - 1));
+        for (int r = 0; r < RB; r++) xres[r] = __ldcg(a.out + rbase + min(gwarp * RB + r, a.rows - 1));
     }
 
     if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red);
@@ -595,7 +666,8 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 if (lane == 0 && row + 1 < a.rows) {
                     const float v1 = val[r], v3 = val[r + 1];
                     const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, exact ? expf_ref(-v1) : expf(-v1)));
-                    a.out[row >> 1] = __fmul_rn(__fmul_rn(v1, sg), v3);
+                    const float hv = __fmul_rn(__fmul_rn(v1, sg), v3);
+                    if (TP) tp_store(a.tp, rbase + (row >> 1), hv); else a.out[row >> 1] = hv;
                 }
             }
         } else {
@@ -604,8 +676,13 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 const uint32_t row = row0 + r;
                 if (row >= a.rows) break;
                 float v = val[r];
-                if (EPI == EPI_STORE) { if (lane == 0) a.out[row] = v; }
-                else if (EPI == EPI_RESID) { if (lane == 0) a.out[row] = __fadd_rn(kFirst ? xres[r] : __ldcg(a.out + row), v); }
+                if (EPI == EPI_STORE) { if (lane == 0) { if (TP) tp_store(a.tp, rbase + row, v); else a.out[row] = v; } }
+                else if (EPI == EPI_RESID) {
+                    if (lane == 0) {
+                        const float xn = __fadd_rn(kFirst ? xres[r] : __ldcg(a.out + rbase + row), v);
+                        if (TP) tp_store(a.tp, rbase + row, xn); else a.out[row] = xn;
+                    }
+                }
                 else if (EPI == EPI_QKV) {
                     if (lane == 0) {
                         if (row < d.q_dim) a.out[row] = v;
@@ -617,9 +694,9 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                     }
                 } else if (EPI == EPI_CLS) {
                     // infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037
-                    if (pen != 1.0f && __ldcg(a.seen + row)) v = __fdiv_rn(v, pen);      // x / 1.0f == x: skip the lookup
-                    if (lane == 0) a.out[row] = v;
-                    if (v > bestv) { bestv = v; besti = row; }
+                    if (pen != 1.0f && __ldcg(a.seen + rbase + row)) v = __fdiv_rn(v, pen);      // x / 1.0f == x: skip the lookup
+                    if (lane == 0) a.out[rbase + row] = v;
+                    if (v > bestv) { bestv = v; besti = rbase + row; }
                 }
             }
         }
@@ -630,6 +707,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     }
 
     NB_STAMP(a.dbg, 5);
+    if (TP && EPI != EPI_QKV && EPI != EPI_CLS) { if (lane == 0) __threadfence_system(); __syncthreads(); }
     if (EPI == EPI_CLS) {
         // rows were visited in ascending order per warp, so (bestv,besti) already holds the warp's first max
         if (lane == 0) { ms.best_v[warp] = bestv; ms.best_i[warp] = besti; }
@@ -646,6 +724,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
 
 // Final argmax over the per-CTA partials + state update, by ONE full CTA.  Returns (in every thread) the token
 // that the next step will consume (device loop) or the sampled token (API mode).
+template <bool TP = false>
 __device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t ncta, MatvecSmem &ms) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float bv = -FLT_MAX; uint32_t bi = 0xffffffffu;
@@ -665,6 +744,22 @@ __device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t n
         bv = -FLT_MAX; bi = 0xffffffffu;
         for (int w = 0; w < kWarps; w++)
             if (ms.best_i[w] != 0xffffffffu && (ms.best_v[w] > bv || (ms.best_v[w] == bv && ms.best_i[w] < bi))) { bv = ms.best_v[w]; bi = ms.best_i[w]; }
+        if (TP) {
+            // all-gather of the per-rank (value, index) pairs through peer memory, then the same ordered pick on every rank
+            const TpArgs &tp = a.tp;
+            TpHdr *h = tp_hdr(tp, tp.rank);
+            const uint32_t base = __ldcg(&h->epoch_base), epoch = base + tp.nph;
+            for (uint32_t p = 0; p < tp.size; p++) { TpHdr *ph = tp_hdr(tp, p); ph->cls_v[tp.rank] = bv; ph->cls_i[tp.rank] = bi; }
+            __threadfence_system();
+            for (uint32_t p = 0; p < tp.size; p++) st_release_sys(&tp_hdr(tp, p)->flags[tp.rank], epoch);
+            for (uint32_t r = 0; r < tp.size; r++) tp_spin(tp, r, epoch);
+            bv = -FLT_MAX; bi = 0xffffffffu;
+            for (uint32_t r = 0; r < tp.size; r++) {
+                const float v = __ldcg(&h->cls_v[r]); const uint32_t i = __ldcg(&h->cls_i[r]);
+                if (i != 0xffffffffu && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+            }
+            h->epoch_base = epoch;
+        }
         if (bi == 0xffffffffu) bi = 0;     // all-NaN row: the reference's argmax returns index 0
         DevState *st = a.st_rw;
         st->cls_ticket = 0;
@@ -684,14 +779,16 @@ __device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t n
     return ms.flag;
 }
 
-template <int QUANT, int EPI, int RB, int LPG>
+template <int QUANT, int EPI, int RB, int LPG, bool TP = false>
 __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(16) unsigned char act[];
     __shared__ MatvecSmem ms;
     pdl_launch_dependents();
     prefetch_row_blocks<QUANT, RB>(a.w, a.rows, a.n, blockIdx.x, gridDim.x, 4);
     pdl_wait();
-    matvec_phase<QUANT, EPI, RB, LPG>(a, blockIdx.x, gridDim.x, act, ms);
+    if (TP) tp_wait(a.tp);
+    matvec_phase<QUANT, EPI, RB, LPG, TP>(a, blockIdx.x, gridDim.x, act, ms);
+    if (TP && EPI != EPI_QKV && EPI != EPI_CLS) tp_publish(a.tp, 0);
     if (EPI == EPI_CLS) {
         if (threadIdx.x == 0) {
             __threadfence();
@@ -701,7 +798,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
         __syncthreads();
         const bool last = ms.flag != 0;
         __syncthreads();
-        if (last) { __threadfence(); cls_finalize(a, gridDim.x, ms); }
+        if (last) { __threadfence(); cls_finalize<TP>(a, gridDim.x, ms); }
     }
 }
 
@@ -796,6 +893,7 @@ struct AttnArgs {
     const DevState *st;
     uint32_t nsplit_max, chunk_cap;
     Dims d;
+    TpArgs tp;               // tensor parallel: xba is pushed to every rank (k_attention_fast<KVM, true>)
 };
 
 // one head vector: optional rmsnorm (Qwen3) + rope; in/out in shared memory; called by one warp
@@ -1036,7 +1134,7 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
 
 // One (kv head, split) item of the grid-wide paths: partial -> HBM workspace; the last CTA of the kv head merges.
 // smem (floats): streaming workspace | wsc[KVM*nsplit_max] | stat[2*KVM]
-template <int KVM, int NT>
+template <int KVM, int NT, bool TP = false>
 __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_t split, uint32_t pos, uint32_t range, uint32_t chunk,
                                           uint32_t nsplit, float *sm, uint32_t &is_last) {
     constexpr int NW = NT / 32;
@@ -1091,12 +1189,14 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
         float o = 0.0f;
 #pragma unroll 4
         for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(__ldcg(a.ws_acc + (base + s2) * hd + i), wsc[m * a.nsplit_max + s2], o);
-        a.xba[(size_t)(g * KVM + m) * hd + i] = __fdiv_rn(o, stat[2 * m]);
+        const float ov = __fdiv_rn(o, stat[2 * m]);
+        if (TP) tp_store(a.tp, a.tp.row_base + (g * KVM + m) * hd + i, ov); else a.xba[(size_t)(g * KVM + m) * hd + i] = ov;
     }
     if (threadIdx.x == 0) a.ticket[g] = 0;
+    if (TP) { __threadfence_system(); __syncthreads(); tp_publish(a.tp, 1); }      // the last of the KV merging CTAs publishes
 }
 
-template <int KVM>
+template <int KVM, bool TP = false>
 __global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {      // same CTA shape as the megakernel => same bits
     extern __shared__ __align__(16) float sm[];
     __shared__ uint32_t is_last;
@@ -1110,7 +1210,7 @@ __global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {
     chunk = min((chunk + 7u) & ~7u, a.chunk_cap);
     const uint32_t nsplit = (range + chunk - 1) / chunk;
     if (blockIdx.x >= nsplit) return;
-    attn_item<KVM, kThreads>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
+    attn_item<KVM, kThreads, TP>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
 }
 
 __global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {

@@ -27,6 +27,7 @@ EXPORTS = [
     "nb200_write_x", "nb200_run_layer", "nb200_profile_tokens", "nb200_trace_token", "nb200_kernel_launches", "nb200_launches_per_token", "nb200_weight_bytes",
     "nb200_op_rmsnorm", "nb200_op_q80_quantize", "nb200_op_q80_matvec", "nb200_op_f32_matvec",
     "nb200_op_q4k_quantize", "nb200_op_q4k_matvec",
+    "nb200_engine_create_tp", "nb200_tp_export", "nb200_tp_attach_ipc", "nb200_tp_attach_local",
 ]
 
 
@@ -53,6 +54,11 @@ def lib():
         L = C.CDLL(path)
         L.nb200_last_error.restype = C.c_char_p
         L.nb200_engine_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32]
+        L.nb200_engine_create_tp.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_uint32,
+                                             C.c_uint32, C.c_uint32]
+        L.nb200_tp_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_tp_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
+        L.nb200_tp_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.nb200_engine_destroy.argtypes = [C.c_void_p]
         L.nb200_get_config.argtypes = [C.c_void_p, C.POINTER(Config)]
         L.nb200_forward.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -99,14 +105,23 @@ def _p(a: np.ndarray, t):
 class Engine:
     """One model resident in the HBM of one B200."""
 
-    def __init__(self, model, max_seq: int, device: int = 0, flags: int = 0):
+    def __init__(self, model, max_seq: int, device: int = 0, flags: int = 0, tp: Optional[Tuple[int, int]] = None):
+        """tp=(rank, size) creates one rank of a tensor-parallel group; attach it (tp_attach_ipc / TpGroup) before use."""
         L = lib()
         if isinstance(model, (str, os.PathLike)):
             image = np.fromfile(model, dtype=np.uint8)
         else:
             image = np.frombuffer(bytes(model), dtype=np.uint8)
         self.h = C.c_void_p()
-        _check(L.nb200_engine_create(C.byref(self.h), image.ctypes.data, image.size, max_seq, device, flags))
+        if tp is None:
+            _check(L.nb200_engine_create(C.byref(self.h), image.ctypes.data, image.size, max_seq, device, flags))
+        else:
+            _check(L.nb200_engine_create_tp(C.byref(self.h), image.ctypes.data, image.size, max_seq, device, flags,
+                                            int(tp[0]), int(tp[1])))
+        self._refresh()
+
+    def _refresh(self):
+        L = lib()
         cfg = Config()
         _check(L.nb200_get_config(self.h, C.byref(cfg)))
         self.cfg = cfg
@@ -116,6 +131,25 @@ class Engine:
         self.path = {3: "cluster-resident kernel (16-CTA cluster, DSMEM activations, TMA weight ring)",
                      2: "persistent megakernel (cooperative launch, L2 grid barriers)",
                      1: "multi-kernel CUDA graph with PDL", 0: "multi-kernel direct launches"}[int(cfg.reserved[0])]
+
+    # ---- tensor parallel ----
+    def tp_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's exchange block (send it to the other ranks' processes)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().nb200_tp_export(self.h, buf))
+        return buf.raw
+
+    def tp_attach_ipc(self, handles) -> None:
+        """handles: the tp_size 64-byte handles in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.tp_size
+        _check(lib().nb200_tp_attach_ipc(self.h, blob))
+        self._refresh()
+
+    def logits_slice(self) -> Tuple[int, int]:
+        """[lo, hi) of the logits this rank computes (the whole vector on one GPU)."""
+        per = self.vocab // self.tp_size
+        return self.tp_rank * per, (self.tp_rank + 1) * per
 
     def close(self):
         if getattr(self, "h", None):
@@ -188,6 +222,63 @@ class Engine:
     @property
     def weight_bytes(self) -> int:
         return int(lib().nb200_weight_bytes(self.h))
+
+
+class TpGroup:
+    """All ranks of a tensor-parallel group inside ONE process (one engine per visible GPU, one host thread per rank
+    for the blocking calls).  Multi-process hosts (one rank per process, e.g. under torchrun) use Engine(tp=...) with
+    tp_export / tp_attach_ipc instead -- see bench.py."""
+
+    def __init__(self, model, max_seq: int, size: int, flags: int = 0, devices=None):
+        if isinstance(model, (str, os.PathLike)):
+            model = np.fromfile(model, dtype=np.uint8).tobytes()
+        devices = list(devices) if devices is not None else list(range(size))
+        self.ranks = [Engine(model, max_seq, device=devices[r], flags=flags, tp=(r, size)) for r in range(size)]
+        arr = (C.c_void_p * size)(*[e.h for e in self.ranks])
+        for e in self.ranks:
+            _check(lib().nb200_tp_attach_local(e.h, arr))
+            e._refresh()
+        self.size = size
+        self.vocab = self.ranks[0].vocab
+
+    def _all(self, fn):
+        import threading
+        out = [None] * self.size; err = [None] * self.size
+
+        def run(r):
+            try:
+                out[r] = fn(self.ranks[r], r)
+            except BaseException as ex:      # noqa: BLE001 - re-raised below
+                err[r] = ex
+        ts = [threading.Thread(target=run, args=(r,)) for r in range(self.size)]
+        for t in ts: t.start()
+        for t in ts: t.join()
+        for ex in err:
+            if ex is not None: raise ex
+        return out
+
+    def forward(self, token: int, pos: int, causal: int = 1) -> np.ndarray:
+        parts = self._all(lambda e, r: e.forward(token, pos, causal))
+        full = np.empty(self.vocab, np.float32)
+        for e, p in zip(self.ranks, parts):
+            lo, hi = e.logits_slice(); full[lo:hi] = p[lo:hi]
+        return full
+
+    def next_greedy(self, ids: np.ndarray, pos: int, prefilling: int, penalty: float = 1.0) -> int:
+        got = self._all(lambda e, r: e.next_greedy(ids, pos, prefilling, penalty))
+        assert len(set(got)) == 1, f"ranks disagree: {got}"
+        return got[0]
+
+    def decode_greedy(self, ids: np.ndarray, n_prompt: int, n_total: int, penalty: float = 1.0):
+        copies = [ids.copy() for _ in range(self.size)]
+        times = self._all(lambda e, r: e.decode_greedy(copies[r], n_prompt, n_total, penalty))
+        for c in copies[1:]:
+            assert np.array_equal(c[:n_total], copies[0][:n_total]), "ranks disagree on the decoded ids"
+        ids[:n_total] = copies[0][:n_total]
+        return max(t[0] for t in times), max(t[1] for t in times)
+
+    def close(self):
+        for e in self.ranks: e.close()
 
 
 # ---- op-level wrappers (host arrays in/out) ----
