@@ -49,6 +49,7 @@ WORKLOADS = {
     "qwen3-4b-q80": ("qwen3-4b", mf.QUANT_Q80, 128, 4096),
     "toy-qwen3-q80": ("toy-qwen3", mf.QUANT_Q80, 64, 128),
 }
+FAST_FILE = {"qwen3-1.7b-q80": True, "qwen3-4b-q80": True}      # multi-GB files: synthesise codes/scales directly (seconds, not minutes)
 PROMPT = 16
 CLASS_NAMES = ["embed", "qkv", "attention", "o_proj", "w13_swiglu", "w2", "classifier"]
 
@@ -262,9 +263,9 @@ def main():
     rank_env = int(os.environ.get("RANK", "0"))
     local_env = int(os.environ.get("LOCAL_RANK", "0"))
     if rank_env == 0 or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) == 1:
-        path = mf.cached_model(spec, quant, gs or 128)
+        path = mf.cached_model(spec, quant, gs or 128, fast=FAST_FILE.get(args.workload, False))
     if args.impl == "reference":
-        path = mf.cached_model(spec, quant, gs or 128)
+        path = mf.cached_model(spec, quant, gs or 128, fast=FAST_FILE.get(args.workload, False))
         run_reference_arm(args, spec, quant, gs, seq, path)
         return
 
@@ -272,7 +273,7 @@ def main():
     rank, world, local, dist = dist_setup(args.gpus)
     if dist is not None:
         dist.barrier()
-    path = mf.cached_model(spec, quant, gs or 128)           # every rank finds the file rank 0 wrote
+    path = mf.cached_model(spec, quant, gs or 128, fast=FAST_FILE.get(args.workload, False))           # every rank finds the file rank 0 wrote
     flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_MEGA if args.no_mega else 0) | (E.FLAG_NO_CLUSTER if args.no_cluster else 0)
     tp = args.mode == "tp" and world > 1
     if tp:

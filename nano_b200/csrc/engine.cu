@@ -234,7 +234,6 @@ int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, 
     const uint32_t cap = (uint32_t)num_sms * grid_mult();
     if (grid > cap) grid = cap;
     if (epi == EPI_CLS && e) { if (grid > e->cls_grid) grid = e->cls_grid; }
-    a.tp.expected = grid;
     return launch<MatvecArgs>(e, k, dim3(grid), dim3(kThreads), smem, a);
 }
 
@@ -250,14 +249,14 @@ TpArgs tp_args(nb200_engine *e, uint32_t wait_ph, uint32_t signal_ph, uint32_t r
     TpArgs t{};
     if (e->tp_size <= 1) return t;
     t.size = e->tp_size; t.rank = e->tp_rank; t.wait_ph = wait_ph; t.signal_ph = signal_ph; t.nph = 4 * e->d.L + 1;
-    t.row_base = row_base; t.out_off = out_off; t.expected = 1;
+    t.row_base = row_base; t.out_off = out_off;
     for (uint32_t p = 0; p < e->tp_size; p++) t.peer[p] = e->tp_peer[p];
     return t;
 }
 
 int run_embed(nb200_engine *e) {
     EmbedArgs a{};
-    a.w = e->emb.w; a.w_aux = e->emb.aux; a.x = e->x; a.ids = e->ids_dev; a.st = e->st; a.d = e->d;
+    a.w = e->emb.w; a.w_aux = e->emb.aux; a.x = e->x; a.ids = e->ids_dev; a.st = e->st; a.d = e->d; a.ll = e->tp_size > 1;
     e->prof_tag = 0;
     return launch<EmbedArgs>(e, k_embed, dim3(1), dim3(256), 0, a);
 }
@@ -287,7 +286,7 @@ int run_layer(nb200_engine *e, uint32_t l) {
         void (*kern)(const AttnArgs) = k_attention;
         uint32_t smem = e->attn_smem;
         const bool tp = e->tp_size > 1;
-        if (tp) { a.tp = tp_args(e, 0, 4 * l + 1, e->tp_rank * d.q_dim, e->tp_off_xba); a.tp.expected = d.KV; }
+        if (tp) a.tp = tp_args(e, 0, 4 * l + 1, e->tp_rank * d.q_dim, e->tp_off_xba);
         if (d.hd <= 128 && (d.arch != 3u || (d.hd & (d.hd - 1)) == 0) && (tp || !getenv("NB200_GENERIC_ATTN"))) {
             switch (d.kv_mul) {
                 case 1: kern = tp ? k_attention_fast<1, true> : k_attention_fast<1>; break;
@@ -863,8 +862,8 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     if (T > 1) {
         // exchange block: the three replicated activation vectors live where the peers can write them
         auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-        e->tp_off_x = kTpHdrBytes; e->tp_off_xba = (uint32_t)(e->tp_off_x + al(E * 4)); e->tp_off_hb = (uint32_t)(e->tp_off_xba + al(QD * 4));
-        e->tp_block_bytes = e->tp_off_hb + al(F * 4);
+        e->tp_off_x = kTpHdrBytes; e->tp_off_xba = (uint32_t)(e->tp_off_x + al(E * 8)); e->tp_off_hb = (uint32_t)(e->tp_off_xba + al(QD * 8));
+        e->tp_block_bytes = e->tp_off_hb + al(F * 8);      // {value, epoch} 64-bit elements
         DM(e->tp_block, e->tp_block_bytes);
         CK(cudaMemset(e->tp_block, 0, e->tp_block_bytes));
         e->x = (float *)(e->tp_block + e->tp_off_x); e->xba = (float *)(e->tp_block + e->tp_off_xba); e->hb = (float *)(e->tp_block + e->tp_off_hb);
@@ -1154,6 +1153,8 @@ int nb200_read_buffer(nb200_engine *e, int field, uint32_t layer, uint32_t pos, 
     CK(cudaStreamSynchronize(e->stream));
     const Dims &d = e->d;
     const float *src = nullptr; uint32_t avail = 0;
+    if (e->tp_size > 1 && (field == NB200_F_X || field == NB200_F_XBA || field == NB200_F_HB))
+        return fail(NB200_EINVAL, "tensor-parallel engines keep x/xba/hb as {value, epoch} words; read them from a single-GPU engine");
     switch (field) {
         case NB200_F_X: src = e->x; avail = d.E; break;
         case NB200_F_XBA: src = e->xba; avail = d.q_dim; break;
@@ -1181,6 +1182,7 @@ int nb200_read_buffer(nb200_engine *e, int field, uint32_t layer, uint32_t pos, 
 
 int nb200_write_x(nb200_engine *e, const float *x, uint32_t count) {
     if (!e || !x || count != e->d.E) return fail(NB200_EINVAL, "bad argument");
+    if (e->tp_size > 1) return fail(NB200_EINVAL, "not available on tensor-parallel engines");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemcpy(e->x, x, (size_t)count * 4, cudaMemcpyHostToDevice));
@@ -1189,6 +1191,7 @@ int nb200_write_x(nb200_engine *e, const float *x, uint32_t count) {
 
 int nb200_run_layer(nb200_engine *e, uint32_t layer, uint32_t pos, uint32_t is_causal) {
     if (!e || layer >= e->d.L || pos >= e->d.max_seq) return fail(NB200_EINVAL, "bad argument");
+    if (e->tp_size > 1) return fail(NB200_EINVAL, "not available on tensor-parallel engines");
     CK(cudaSetDevice(e->device));
     int r;
     if ((r = push_state(e, pos, is_causal ? 1u : 0u, 0, 0, 1.0f, 0, 1))) return r;

@@ -54,20 +54,23 @@ struct DevState {
 // ------------------------------------------------------------------------------------------------
 // Tensor parallelism over NVLink peer memory (there is no reference code for this, the reference is one CPU).
 // Every rank owns a row slice of each matrix (whole kv-head groups for QKV/attention) and keeps the FULL activation
-// vectors x / xba / hb in an "exchange block" that its peers can write.  A producing kernel's epilogue pushes each
-// finished element into every peer's copy (plain st.global over NVLink, no remote reads anywhere), then the last CTA
-// publishes an epoch number into every peer's flag word; the consuming kernel spins on its LOCAL flag words.  Row dots
-// are computed exactly as on one GPU and every rank quantises the same full vector, so results are bit-identical to
-// the single-GPU engine.
+// vectors x / xba / hb in an "exchange block" that its peers can write.  Each element of those vectors is a 64-bit word
+// {fp32 value, 32-bit epoch}: a producing kernel's epilogue pushes every finished element into every rank's copy with ONE
+// 8-byte store (single-copy atomic, so the value and its epoch arrive together -- no fence, no flag, no ticket), and the
+// consuming kernel's activation prologue spins per element until the epoch it expects has arrived.  Nothing is ever read
+// remotely.  The epoch of exchange k of token t is t*nph + k, so a buffer reused by a later exchange can never be
+// mistaken for the earlier one.  Row dots are computed exactly as on one GPU and every rank prepares the same full
+// vector, so results are bit-identical to the single-GPU engine.
+//   Why a buffer is never overwritten before its readers are done (no double buffering): a rank can only start the
+//   exchange that rewrites x / xba / hb after it has consumed, from EVERY rank, the elements of a later exchange whose
+//   producing kernels run (in stream order) after the kernels that read the old contents.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTpMax = 8;
 struct TpHdr {                     // first 256 bytes of the exchange block
-    uint32_t flags[kTpMax];        // flags[r]: last epoch rank r published to me
-    uint32_t epoch_base;           // phases completed by earlier tokens (local; bumped by the classifier's last CTA)
-    uint32_t ticket[2];            // last-CTA election of the publishing kernel (local)
-    uint32_t timeout;              // set when a spin gave up (peer died): results are garbage, host reports an error
-    float cls_v[kTpMax];           // per-rank argmax partials (written by peers)
-    uint32_t cls_i[kTpMax];
+    unsigned long long cls_v[kTpMax];   // per-rank argmax partials {value bits, epoch} / {index, epoch} (written by peers)
+    unsigned long long cls_i[kTpMax];
+    uint32_t epoch_base;           // exchanges completed by earlier tokens (local; bumped by the classifier's last CTA)
+    uint32_t timeout;              // set when a spin gave up (peer died): results are garbage, the host reports an error
 };
 constexpr uint32_t kTpHdrBytes = 256;
 struct TpArgs {
@@ -75,49 +78,36 @@ struct TpArgs {
     uint32_t wait_ph, signal_ph;   // 1-based exchange ids within a token (0 = none); epoch = epoch_base + id
     uint32_t nph;                  // exchanges per token
     uint32_t row_base;             // global index of local output row 0
-    uint32_t out_off;              // byte offset of the output vector inside the exchange block
-    uint32_t expected;             // CTAs that take part in the publishing election
+    uint32_t out_off;              // byte offset of the output vector (64-bit elements) inside the exchange block
+    uint32_t pad;
     unsigned char *peer[kTpMax];   // exchange block of every rank (peer[rank] = own)
 };
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ TpHdr *tp_hdr(const TpArgs &tp, uint32_t r) { return reinterpret_cast<TpHdr *>(tp.peer[r]); }
-// spin until rank r's flag in MY block reaches `need`; gives up after ~4 s so a dead peer cannot hang the GPU
-__device__ __forceinline__ void tp_spin(const TpArgs &tp, uint32_t r, uint32_t need) {
-    TpHdr *h = tp_hdr(tp, tp.rank);
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(&h->flags[r]) - need) < 0) {
-        if (clock64() - t0 > 8000000000ll) { h->timeout = 1; break; }
+__device__ __forceinline__ unsigned long long tp_pack(uint32_t bits, uint32_t epoch) { return ((unsigned long long)epoch << 32) | bits; }
+// spin until the 64-bit element carries an epoch >= need; gives up after ~4 s so a dead peer cannot hang the GPU
+__device__ __forceinline__ uint32_t tp_spin_load(const TpArgs &tp, const unsigned long long *p, uint32_t need) {
+    unsigned long long w = ld_relaxed_sys_u64(p);
+    if ((int32_t)((uint32_t)(w >> 32) - need) < 0) {
+        const long long t0 = clock64();
+        do {
+            w = ld_relaxed_sys_u64(p);
+            if (clock64() - t0 > 8000000000ll) { tp_hdr(tp, tp.rank)->timeout = 1; break; }
+        } while ((int32_t)((uint32_t)(w >> 32) - need) < 0);
     }
+    return (uint32_t)w;
 }
-// consumer side: threads 0..size-1 each wait for one producer rank; the CTA continues after the barrier
-__device__ __forceinline__ void tp_wait(const TpArgs &tp) {
-    if (tp.wait_ph && threadIdx.x < tp.size) tp_spin(tp, threadIdx.x, __ldcg(&tp_hdr(tp, tp.rank)->epoch_base) + tp.wait_ph);
-    __syncthreads();
+// push one finished element (with its epoch) into every rank's copy of the output vector
+__device__ __forceinline__ void tp_store(const TpArgs &tp, uint32_t idx, float v, uint32_t epoch) {
+    const unsigned long long w = tp_pack(__float_as_uint(v), epoch);
+    for (uint32_t p = 0; p < tp.size; p++) st_relaxed_sys_u64(reinterpret_cast<unsigned long long *>(tp.peer[p] + tp.out_off) + idx, w);
 }
-// push one finished element into every rank's copy of the output vector
-__device__ __forceinline__ void tp_store(const TpArgs &tp, uint32_t idx, float v) {
-    for (uint32_t p = 0; p < tp.size; p++) reinterpret_cast<float *>(tp.peer[p] + tp.out_off)[idx] = v;
-}
-// producer side, end of kernel.  Precondition: every thread that called tp_store has executed __threadfence_system()
-// and the CTA has synchronised.  The last of `expected` CTAs publishes the epoch to every rank.
-__device__ __forceinline__ void tp_publish(const TpArgs &tp, uint32_t slot) {
-    if (threadIdx.x == 0) {
-        TpHdr *h = tp_hdr(tp, tp.rank);
-        __threadfence();
-        const uint32_t t = atomicAdd(&h->ticket[slot], 1u);
-        if (t == tp.expected - 1) {
-            h->ticket[slot] = 0;
-            __threadfence_system();
-            const uint32_t epoch = __ldcg(&h->epoch_base) + tp.signal_ph;
-            for (uint32_t p = 0; p < tp.size; p++) st_release_sys(&tp_hdr(tp, p)->flags[tp.rank], epoch);
-        }
-    }
-}
+__device__ __forceinline__ uint32_t tp_epoch(const TpArgs &tp, uint32_t ph) { return __ldcg(&tp_hdr(tp, tp.rank)->epoch_base) + ph; }
 
 enum Epilogue { EPI_STORE = 0, EPI_QKV = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_CLS = 4 };
 
@@ -203,11 +193,18 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // Stage the fp32 source vector into shared memory with L2 (.cg) loads: the vector was produced by other
 // CTAs (another kernel, or another phase of the persistent kernel), so it must not come from L1 / the
 // non-coherent path.
-template <int NT>
-__device__ __forceinline__ void stage_vector(const float *src, const float *__restrict__ gain, int n, float *stage) {
+// LL (tensor parallel): src is a vector of {value, epoch} words; spin per element until exchange tp->wait_ph has landed.
+template <int NT, bool LL = false>
+__device__ __forceinline__ void stage_vector(const float *src, const float *__restrict__ gain, int n, float *stage, const TpArgs *tp = nullptr) {
     float *gstage = stage + n;                       // the rmsnorm gain rides along (one L2 latency, not two)
+    uint32_t need = 0;
+    if (LL && tp->wait_ph) need = tp_epoch(*tp, tp->wait_ph);
     for (int i = threadIdx.x; i < n; i += NT) {
-        const float v = __ldcg(src + i);
+        float v;
+        if (LL) {
+            const unsigned long long *e = reinterpret_cast<const unsigned long long *>(src) + i;
+            v = __uint_as_float(tp->wait_ph ? tp_spin_load(*tp, e, need) : (uint32_t)__ldcg(e));
+        } else v = __ldcg(src + i);
         const float g = gain ? __ldg(gain + i) : 0.0f;
         stage[i] = v;
         if (gain) gstage[i] = g;
@@ -261,9 +258,10 @@ __host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, u
     return act_region_bytes(quant, n, gs) + 2u * n * 4u;      // + staging copies of the source and the gain
 }
 
-template <int NT>
-__device__ void prep_f32(const float *src, const float *__restrict__ gain, int n, bool exact, float *act, float *stage, float *red) {
-    stage_vector<NT>(src, gain, n, stage);
+template <int NT, bool LL = false>
+__device__ void prep_f32(const float *src, const float *__restrict__ gain, int n, bool exact, float *act, float *stage, float *red,
+                         const TpArgs *tp = nullptr) {
+    stage_vector<NT, LL>(src, gain, n, stage, tp);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(stage, n, gain != nullptr, inv, i);
@@ -282,13 +280,13 @@ __device__ __forceinline__ int q80_code(float v, float sc, float rinv) {
 }
 
 // tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
-template <int NT>
+template <int NT, bool LL = false>
 __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n, int gs, bool exact,
                          unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales,
-                         unsigned long long *dbg = nullptr) {
+                         unsigned long long *dbg = nullptr, const TpArgs *tp = nullptr) {
     int8_t *codes = reinterpret_cast<int8_t *>(act);
     float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
-    stage_vector<NT>(src, gain, n, stage);
+    stage_vector<NT, LL>(src, gain, n, stage, tp);
     NB_STAMP(dbg, 2);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
@@ -324,13 +322,13 @@ __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n
 //   dump_scales[0..n/256)      = ss
 //   dump_scales[n/256..2n/256) = sbias
 //   dump_codes[n .. n + n/32)  = s6, dump_codes[n + n/32 .. n + 2n/32) = b6
-template <int NT>
+template <int NT, bool LL = false>
 __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n, bool exact,
-                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales) {
+                         unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales, const TpArgs *tp = nullptr) {
     uint32_t *xe = reinterpret_cast<uint32_t *>(act);
     uint32_t *xo = reinterpret_cast<uint32_t *>(act + n / 2);
     float4 *gp = reinterpret_cast<float4 *>(act + n);
-    stage_vector<NT>(src, gain, n, stage);
+    stage_vector<NT, LL>(src, gain, n, stage, tp);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -611,6 +609,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     const Dims &d = a.d;
     // tensor parallel: local row r is element rbase + r of the (replicated) output vector; QKV outputs stay local
     const uint32_t rbase = (TP && EPI != EPI_QKV) ? a.tp.row_base : 0u;
+    const unsigned long long *out_ll = reinterpret_cast<const unsigned long long *>(a.out);     // TP: x is {value, epoch} words
     const bool exact = d.exact != 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nblocks = (a.rows + RB - 1) / RB;
@@ -626,12 +625,17 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
         q80_load<RB, LPG>(pre, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), gwarp * RB, a.rows, a.n, 0);
     if (EPI == EPI_RESID && has_first) {
 #pragma unroll
-        for (int r = 0; r < RB; r++) xres[r] = __ldcg(a.out + rbase + min(gwarp * RB + r, a.rows - 1));
+        for (int r = 0; r < RB; r++) {
+            const uint32_t xi = rbase + min(gwarp * RB + r, a.rows - 1);
+            xres[r] = TP ? __uint_as_float((uint32_t)__ldcg(out_ll + xi)) : __ldcg(a.out + xi);       // own rows: written by this rank
+        }
     }
 
-    if (QUANT == 0x00) prep_f32<kThreads>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red);
-    else if (QUANT == 0x80) { NB_STAMP(a.dbg, 1); prep_q80<kThreads>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, a.dbg); }
-    else prep_q4k<kThreads>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales);
+    if (QUANT == 0x00) prep_f32<kThreads, TP>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red, &a.tp);
+    else if (QUANT == 0x80) { NB_STAMP(a.dbg, 1); prep_q80<kThreads, TP>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, a.dbg, &a.tp); }
+    else prep_q4k<kThreads, TP>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, &a.tp);
+    uint32_t out_epoch = 0;
+    if (TP && a.tp.signal_ph) out_epoch = tp_epoch(a.tp, a.tp.signal_ph);
 
     NB_STAMP(a.dbg, 4);
     const uint32_t pos = a.state_known ? a.pos_val : (a.st ? __ldcg(&a.st->pos) : 0);
@@ -667,7 +671,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                     const float v1 = val[r], v3 = val[r + 1];
                     const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, exact ? expf_ref(-v1) : expf(-v1)));
                     const float hv = __fmul_rn(__fmul_rn(v1, sg), v3);
-                    if (TP) tp_store(a.tp, rbase + (row >> 1), hv); else a.out[row >> 1] = hv;
+                    if (TP) tp_store(a.tp, rbase + (row >> 1), hv, out_epoch); else a.out[row >> 1] = hv;
                 }
             }
         } else {
@@ -676,11 +680,12 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 const uint32_t row = row0 + r;
                 if (row >= a.rows) break;
                 float v = val[r];
-                if (EPI == EPI_STORE) { if (lane == 0) { if (TP) tp_store(a.tp, rbase + row, v); else a.out[row] = v; } }
+                if (EPI == EPI_STORE) { if (lane == 0) { if (TP) tp_store(a.tp, rbase + row, v, out_epoch); else a.out[row] = v; } }
                 else if (EPI == EPI_RESID) {
                     if (lane == 0) {
-                        const float xn = __fadd_rn(kFirst ? xres[r] : __ldcg(a.out + rbase + row), v);
-                        if (TP) tp_store(a.tp, rbase + row, xn); else a.out[row] = xn;
+                        const float xo = kFirst ? xres[r] : (TP ? __uint_as_float((uint32_t)__ldcg(out_ll + rbase + row)) : __ldcg(a.out + rbase + row));
+                        const float xn = __fadd_rn(xo, v);
+                        if (TP) tp_store(a.tp, rbase + row, xn, out_epoch); else a.out[row] = xn;
                     }
                 }
                 else if (EPI == EPI_QKV) {
@@ -707,7 +712,6 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
     }
 
     NB_STAMP(a.dbg, 5);
-    if (TP && EPI != EPI_QKV && EPI != EPI_CLS) { if (lane == 0) __threadfence_system(); __syncthreads(); }
     if (EPI == EPI_CLS) {
         // rows were visited in ascending order per warp, so (bestv,besti) already holds the warp's first max
         if (lane == 0) { ms.best_v[warp] = bestv; ms.best_i[warp] = besti; }
@@ -748,14 +752,14 @@ __device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t n
             // all-gather of the per-rank (value, index) pairs through peer memory, then the same ordered pick on every rank
             const TpArgs &tp = a.tp;
             TpHdr *h = tp_hdr(tp, tp.rank);
-            const uint32_t base = __ldcg(&h->epoch_base), epoch = base + tp.nph;
-            for (uint32_t p = 0; p < tp.size; p++) { TpHdr *ph = tp_hdr(tp, p); ph->cls_v[tp.rank] = bv; ph->cls_i[tp.rank] = bi; }
-            __threadfence_system();
-            for (uint32_t p = 0; p < tp.size; p++) st_release_sys(&tp_hdr(tp, p)->flags[tp.rank], epoch);
-            for (uint32_t r = 0; r < tp.size; r++) tp_spin(tp, r, epoch);
+            const uint32_t epoch = __ldcg(&h->epoch_base) + tp.nph;
+            for (uint32_t p = 0; p < tp.size; p++) {
+                st_relaxed_sys_u64(&tp_hdr(tp, p)->cls_v[tp.rank], tp_pack(__float_as_uint(bv), epoch));
+                st_relaxed_sys_u64(&tp_hdr(tp, p)->cls_i[tp.rank], tp_pack(bi, epoch));
+            }
             bv = -FLT_MAX; bi = 0xffffffffu;
             for (uint32_t r = 0; r < tp.size; r++) {
-                const float v = __ldcg(&h->cls_v[r]); const uint32_t i = __ldcg(&h->cls_i[r]);
+                const float v = __uint_as_float(tp_spin_load(tp, &h->cls_v[r], epoch)); const uint32_t i = tp_spin_load(tp, &h->cls_i[r], epoch);
                 if (i != 0xffffffffu && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
             }
             h->epoch_base = epoch;
@@ -786,9 +790,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
     pdl_launch_dependents();
     prefetch_row_blocks<QUANT, RB>(a.w, a.rows, a.n, blockIdx.x, gridDim.x, 4);
     pdl_wait();
-    if (TP) tp_wait(a.tp);
     matvec_phase<QUANT, EPI, RB, LPG, TP>(a, blockIdx.x, gridDim.x, act, ms);
-    if (TP && EPI != EPI_QKV && EPI != EPI_CLS) tp_publish(a.tp, 0);
+
     if (EPI == EPI_CLS) {
         if (threadIdx.x == 0) {
             __threadfence();
@@ -847,6 +850,7 @@ __global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
 struct EmbedArgs {
     const void *w; const void *w_aux;   // same layouts as MatvecArgs (classifier/embedding table)
     float *x; const uint32_t *ids; const DevState *st; Dims d;
+    uint32_t ll;                        // tensor parallel: x is a vector of {value, epoch} words (epoch unused for the local embedding)
 };
 
 __global__ void __launch_bounds__(256) k_embed(const EmbedArgs a) {
@@ -873,7 +877,7 @@ __global__ void __launch_bounds__(256) k_embed(const EmbedArgs a) {
             const uint32_t b6 = (g < 4) ? (bb & 0x3f) : ((((bb >> 6) << 4) | (bh >> 4)) & 0x3f);
             v = __fsub_rn(__fmul_rn((float)c, __fmul_rn((float)s6, ss)), __fmul_rn((float)b6, sbi));   // tensor.c:274
         }
-        a.x[i] = v;
+        if (a.ll) reinterpret_cast<unsigned long long *>(a.x)[i] = tp_pack(__float_as_uint(v), 0); else a.x[i] = v;
     }
 }
 
@@ -1183,6 +1187,8 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
         if (lane == 0) stat[2 * warp] = L;
     }
     __syncthreads();
+    uint32_t out_epoch = 0;
+    if (TP) out_epoch = tp_epoch(a.tp, a.tp.signal_ph);
     for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
         const size_t base = (size_t)(g * KVM + m) * a.nsplit_max;
@@ -1190,10 +1196,9 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
 #pragma unroll 4
         for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(__ldcg(a.ws_acc + (base + s2) * hd + i), wsc[m * a.nsplit_max + s2], o);
         const float ov = __fdiv_rn(o, stat[2 * m]);
-        if (TP) tp_store(a.tp, a.tp.row_base + (g * KVM + m) * hd + i, ov); else a.xba[(size_t)(g * KVM + m) * hd + i] = ov;
+        if (TP) tp_store(a.tp, a.tp.row_base + (g * KVM + m) * hd + i, ov, out_epoch); else a.xba[(size_t)(g * KVM + m) * hd + i] = ov;
     }
     if (threadIdx.x == 0) a.ticket[g] = 0;
-    if (TP) { __threadfence_system(); __syncthreads(); tp_publish(a.tp, 1); }      // the last of the KV merging CTAs publishes
 }
 
 template <int KVM, bool TP = false>

@@ -197,7 +197,7 @@ def _rope_table(block: int, hd: int, theta: float = 10000.0):
 
 
 def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int = 39,
-                cls_gain: float = 1.0) -> dict:
+                cls_gain: float = 1.0, fast: bool = False) -> dict:
     """Write a synthetic model file. Weights ~ N(0, 0.02^2) (wo, w3: 0.02/sqrt(2L)), norm gains 1+N(0,0.02^2),
     tied classifier. Returns {'path','bytes','spec','quant','gs'}.
     `cls_gain` scales the embedding/classifier rows (bigger top-1 margins for greedy tests)."""
@@ -219,6 +219,14 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
     def normal(n, std):
         return (rng.standard_normal(n, dtype=np.float32) * np.float32(std)).astype(np.float32)
 
+    def synth_q80(d, n, sd):
+        """fast=True (multi-GB bench files): draw int8 codes and group scales directly instead of quantising floats.
+        Same byte layout and value range as a quantised N(0, sd^2) tensor (max-abs of a 128-group ~ 2.7 sd)."""
+        q = rng.integers(-127, 128, size=d * n, dtype=np.int8)
+        s = (np.float32(2.7 * sd / 127.0) * (np.float32(0.8) + np.float32(0.4) * rng.random(d * n // gs, dtype=np.float32))).astype(np.float32)
+        return q, s
+    assert not fast or quant == QUANT_Q80, "fast synthesis is implemented for Q80 files"
+
     std = 0.02
     std_o = 0.02 / math.sqrt(2 * L)
     tensors = [("wq", Q, E, std), ("wk", K, E, std), ("wv", K, E, std), ("wo", E, Q, std_o),
@@ -231,8 +239,11 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
         f.write((np.float32(1.0) + normal(L * E, 0.02)).tobytes())
         f.write((np.float32(1.0) + normal(E, 0.02)).tobytes())
 
-        emb = normal(V * E, std * cls_gain).reshape(V, E)
-        if quant == QUANT_F32:
+        emb = None if fast else normal(V * E, std * cls_gain).reshape(V, E)
+        if fast:
+            q, s = synth_q80(V, E, std * cls_gain)
+            f.write(q.tobytes()); f.write(s.tobytes())
+        elif quant == QUANT_F32:
             f.write(emb.tobytes())
         elif quant == QUANT_Q80:
             q, s = quantize_q80(emb, gs)
@@ -246,6 +257,10 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
             if quant == QUANT_Q4K:
                 f.write(q4k_frame((L, d, n), L * d * (n // 256)))
             for _l in range(L):
+                if fast:
+                    q, s = synth_q80(d, n, sd)
+                    f.write(q.tobytes()); f.write(s.tobytes())
+                    continue
                 w = normal(d * n, sd).reshape(d, n)
                 if quant == QUANT_F32:
                     f.write(w.tobytes())
@@ -270,16 +285,16 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
 
 
 def cached_model(spec: ModelSpec, quant: int, gs: int = 128, seed: int = 39, cache_dir: Optional[str] = None,
-                 cls_gain: float = 1.0) -> str:
+                 cls_gain: float = 1.0, fast: bool = False) -> str:
     """Write (once) into a cache directory and return the path."""
     cache_dir = cache_dir or os.environ.get("NB200_MODEL_CACHE", "/tmp/nb200_models")
     os.makedirs(cache_dir, exist_ok=True)
     qn = {QUANT_F32: "f32", QUANT_Q80: f"q80g{gs}", QUANT_Q4K: "q4k"}[quant]
-    g = "" if cls_gain == 1.0 else f"_cg{cls_gain:g}"
+    g = ("" if cls_gain == 1.0 else f"_cg{cls_gain:g}") + ("_fast" if fast else "")
     path = os.path.join(cache_dir, f"{spec.name}_{qn}_s{seed}{g}.bin")
     if not os.path.exists(path):
         tmp = path + f".tmp{os.getpid()}"
-        write_model(tmp, spec, quant, gs, seed, cls_gain)
+        write_model(tmp, spec, quant, gs, seed, cls_gain, fast)
         os.replace(tmp, path)
     return path
 
