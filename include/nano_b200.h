@@ -149,6 +149,11 @@ int nb200_op_f32_matvec(float *out, const float *x, const float *w, uint32_t n, 
 /* blocks: 160-byte Q4K blocks in file layout (tensor.h:96-105) */
 int nb200_op_q4k_quantize(uint8_t *blocks, const float *x, uint32_t n);
 int nb200_op_q4k_matvec(float *out, const float *x, const uint8_t *w_blocks, uint32_t n, uint32_t d);
+/* whole-tensor forms on the reference's 160-byte block layout (tensor.h:96-114):
+ *   nb200_op_q4k_quantize_blocks <- quantize_tensor_q4k_in_situ  infer/tensor.c:281-310 (rows % 256 == 0)
+ *   nb200_op_q4k_matvec_blocks   <- matmul_q4k                   infer/tensor.c:438-471 (x already quantised) */
+int nb200_op_q4k_quantize_blocks(uint8_t *blocks, const float *x, uint64_t nblocks);
+int nb200_op_q4k_matvec_blocks(float *out, const uint8_t *x_blocks, const uint8_t *w_blocks, uint32_t n, uint32_t d);
 
 #ifdef __cplusplus
 }

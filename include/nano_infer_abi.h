@@ -144,9 +144,11 @@ uint8_t *make_q4k_tensor(uint32_t ndim, uint32_t shape[]);
 void dequantize_tensor_q4k(uint8_t *Q, float *t_out, uint32_t *ndim, uint32_t *shape);
 uint8_t *pack_q4k_tensor(uint8_t *Q);
 uint8_t *unpack_q4k_tensor(uint8_t *buffer, uint64_t *p_total_bytes);
-/* not provided yet (only infer/tools/export_q4k.c calls them): quantize_tensor_q4k,
- * quantize_tensor_q4k_in_situ, matmul_q4k with pre-quantised host blocks.  The GPU equivalents that take fp32
- * input are nb200_op_q4k_quantize / nb200_op_q4k_matvec. */
+uint8_t *quantize_tensor_q4k(float *t, uint32_t ndim, uint32_t shape[]);                     /* tensor.h:160 */
+void quantize_tensor_q4k_in_situ(float *t, uint32_t ndim, uint32_t shape[], uint8_t *T);     /* tensor.h:161 */
+void matmul_q4k(float *xout, uint8_t *x, uint8_t *w, uint32_t layer);                        /* tensor.h:166 */
+/* The three above run on the GPU (nb200_op_q4k_quantize_blocks / nb200_op_q4k_matvec_blocks) and need last
+ * dimensions that are multiples of 256 (the reference's partial-block path is broken, tensor.c:307). */
 
 /* ---- imported from the reference's unchanged host objects at link time (utils.c, tokenizer.c, hal_ram_linux.c) ---- */
 void *platform_calloc(size_t n, size_t sizeoftype);

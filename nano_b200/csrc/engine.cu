@@ -1371,6 +1371,44 @@ int nb200_op_q4k_matvec(float *out, const float *x, const uint8_t *w_blocks, uin
     return op_matvec(0x42u, out, x, w_blocks, 0, nullptr, 0, n, d, 32, 0, true);
 }
 
+// Whole-tensor Q4K quantisation (quantize_tensor_q4k_in_situ, tensor.c:281-310): `x` holds nblocks*256 floats whose rows
+// are multiples of 256 long; `blocks` receives nblocks 160-byte reference blocks.  Streams through the GPU in chunks.
+int nb200_op_q4k_quantize_blocks(uint8_t *blocks, const float *x, uint64_t nblocks) {
+    if (!blocks || !x || !nblocks) return fail(NB200_EINVAL, "bad argument");
+    int r;
+    if ((r = need_device())) return r;
+    const uint64_t chunk = 1ull << 16;         // 64 Ki blocks = 64 MB of floats per pass
+    DevBuf dx, db;
+    const uint64_t cap = nblocks < chunk ? nblocks : chunk;
+    if ((r = dx.alloc(cap * 1024)) || (r = db.alloc(cap * 160))) return r;
+    for (uint64_t b0 = 0; b0 < nblocks; b0 += chunk) {
+        const uint64_t nb = (nblocks - b0 < chunk) ? nblocks - b0 : chunk;
+        CK(cudaMemcpy(dx.p, x + b0 * 256, nb * 1024, cudaMemcpyHostToDevice));
+        const uint32_t grid = (uint32_t)((nb + 7) / 8 > 4736 ? 4736 : (nb + 7) / 8);
+        k_q4k_quantize_blocks<<<grid, 256>>>(dx.as<float>(), nb, db.as<uint8_t>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(blocks + b0 * 160, db.p, nb * 160, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// matmul_q4k (tensor.c:438-471) with BOTH operands in the reference block layout: x_blocks = n/256 blocks,
+// w_blocks = d rows of n/256 blocks (the caller applies the layer offset).
+int nb200_op_q4k_matvec_blocks(float *out, const uint8_t *x_blocks, const uint8_t *w_blocks, uint32_t n, uint32_t d) {
+    if (!out || !x_blocks || !w_blocks || !n || !d || n % 256) return fail(NB200_EINVAL, "bad argument (n %% 256 != 0?)");
+    int r;
+    if ((r = need_device())) return r;
+    const uint32_t bpr = n / 256;
+    DevBuf dx, dw, dout;
+    if ((r = dx.alloc((size_t)bpr * 160)) || (r = dw.alloc((size_t)d * bpr * 160)) || (r = dout.alloc((size_t)d * 4))) return r;
+    CK(cudaMemcpy(dx.p, x_blocks, (size_t)bpr * 160, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw.p, w_blocks, (size_t)d * bpr * 160, cudaMemcpyHostToDevice));
+    k_q4k_matvec_blocks<<<(d + 7) / 8, 256>>>(dw.as<uint8_t>(), dx.as<uint8_t>(), d, bpr, dout.as<float>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, (size_t)d * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // host-side evaluation of the exact-mode expf (no GPU needed): lets CPU tests pin it to libm
 float nb200_host_expf_ref(float x) { return nb::expf_ref_impl(x); }
 void nb200_host_expf_ref_array(float *dst, const float *src, uint64_t n) { for (uint64_t i = 0; i < n; i++) dst[i] = nb::expf_ref_impl(src[i]); }

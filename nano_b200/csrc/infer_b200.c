@@ -406,6 +406,40 @@ uint8_t *make_q4k_tensor(uint32_t ndim, uint32_t shape[]) {
     return T;
 }
 
+/* tensor.c:281-310 on the GPU.  Every 256-element block of a "line" (last dimension) is quantised independently; lines
+ * whose length is not a multiple of 256 are refused: the reference's own partial-block source offset (`t + i*line_dim +
+ * j*d`, tensor.c:307) is only right for such lines when they are shorter than one block. */
+void quantize_tensor_q4k_in_situ(float *t, uint32_t ndim, uint32_t shape[], uint8_t *T) {
+    if (!t || !T || ndim == 0 || ndim > 6 || rd32(T + 12) != ndim) die("quantize_tensor_q4k_in_situ: bad tensor");
+    const uint32_t line = shape[ndim - 1];
+    if (line == 0 || line % 256u) die("quantize_tensor_q4k_in_situ: last dimension must be a multiple of 256");
+    uint64_t lines = 1;
+    for (uint32_t i = 0; i + 1 < ndim; i++) lines *= shape[i];
+    for (uint32_t i = 0; i < ndim; i++) memcpy(T + 16 + 4 * i, &shape[i], 4);
+    const uint64_t nb = lines * (line / 256u);
+    if (nb != rd32(T + 40)) die("quantize_tensor_q4k_in_situ: block count mismatch");
+    if (nb200_op_q4k_quantize_blocks(T + 44, t, nb) != NB200_OK) die("quantize_tensor_q4k_in_situ");
+}
+
+uint8_t *quantize_tensor_q4k(float *t, uint32_t ndim, uint32_t shape[]) {          /* tensor.c:312-316 */
+    uint8_t *T = make_q4k_tensor(ndim, shape);
+    quantize_tensor_q4k_in_situ(t, ndim, shape, T);
+    return T;
+}
+
+/* tensor.c:438-471: W(d,n) or W(l,d,n)[layer] times an already-quantised x(n); host pointers in and out */
+void matmul_q4k(float *xout, uint8_t *x, uint8_t *w, uint32_t layer) {
+    const uint32_t wdim = rd32(w + 12);
+    if (wdim != 2 && wdim != 3) die("matmul_q4k: weight tensor must have 2 or 3 dimensions");
+    const uint32_t l = (wdim == 3) ? rd32(w + 16) : 1u, d = rd32(w + 16 + 4 * (wdim - 2)), n = rd32(w + 16 + 4 * (wdim - 1));
+    if (rd32(x + 16) != n) die("matmul_q4k: x length differs from the weight's last dimension");
+    if (wdim == 2) layer = 0;
+    if (layer >= l) die("matmul_q4k: layer out of range");
+    if (n % 256u) die("matmul_q4k: last dimension must be a multiple of 256");
+    const uint64_t bpr = n / 256u;
+    if (nb200_op_q4k_matvec_blocks(xout, x + 44, w + 44 + (uint64_t)layer * d * bpr * 160ull, n, d) != NB200_OK) die("matmul_q4k");
+}
+
 uint8_t *pack_q4k_tensor(uint8_t *Q) { return Q; }
 uint8_t *unpack_q4k_tensor(uint8_t *buffer, uint64_t *p_total_bytes) { memcpy(p_total_bytes, buffer, 8); return buffer; }
 

@@ -317,6 +317,42 @@ __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n
     }
 }
 
+// quantize_one_block_q4k_in_situ (tensor.c:144-242) by one warp: lane l holds elements 8l..8l+7 of the 256-element block
+// (group g = lanes 4g..4g+3).  Returns the 4-bit codes of the lane's elements, the group's code sum and 6-bit
+// scale/bias codes (replicated in the 4 lanes of the group) and the block's two fp32 super-scales (all lanes).
+__device__ __forceinline__ void q4k_quantize_block(const float (&v)[8], uint32_t (&c)[8], int &csum, float &ss, float &sbias, int &s6, int &b6) {
+    float lo = FLT_MAX, hi = kTrueMin;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (v[j] > hi) hi = v[j];
+        if (v[j] < lo) lo = v[j];
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    const float s = (lo <= 0.0f) ? __fdiv_rn(__fsub_rn(hi, lo), 15.0f) : __fdiv_rn(hi, 15.0f);
+    const float bias = (lo <= 0.0f) ? -lo : 0.0f;
+    csum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = (s == 0.0f) ? 0u : (uint32_t)(nearest_int_magic(__fdiv_rn(__fadd_rn(v[j], bias), s)) & 0x0f);
+        csum += (int)c[j];
+    }
+    csum += __shfl_xor_sync(0xffffffffu, csum, 1);
+    csum += __shfl_xor_sync(0xffffffffu, csum, 2);
+    float smax = fmaxf(kTrueMin, s), bmax = fmaxf(kTrueMin, bias);
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+        smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    }
+    ss = __fdiv_rn(smax, 63.0f); sbias = __fdiv_rn(bmax, 63.0f);
+    s6 = (ss == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(s, ss)) & 0x3f);
+    b6 = (sbias == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(bias, sbias)) & 0x3f);
+}
+
 // tensor.c:144-242 on 256-element blocks (n % 256 == 0); one warp per block, 8 elements per lane.
 // dump (optional, CTA 0): codes[n] as bytes, then per group {s6,b6} and per block {ss,sbias} in dump_scales:
 //   dump_scales[0..n/256)      = ss
@@ -336,39 +372,13 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
     const bool dump = dump_codes && blockIdx.x == 0;
     for (int b = warp; b < NB; b += NT / 32) {
         float v[8];
-        float lo = FLT_MAX, hi = kTrueMin;
         const int base = b * 256 + lane * 8;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            v[j] = act_value(stage, n, gain != nullptr, inv, base + j);
-            if (v[j] > hi) hi = v[j];
-            if (v[j] < lo) lo = v[j];
-        }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        }
-        const float s = (lo <= 0.0f) ? __fdiv_rn(__fsub_rn(hi, lo), 15.0f) : __fdiv_rn(hi, 15.0f);
-        const float bias = (lo <= 0.0f) ? -lo : 0.0f;
+        for (int j = 0; j < 8; j++) v[j] = act_value(stage, n, gain != nullptr, inv, base + j);
         uint32_t c[8];
-        int csum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            c[j] = (s == 0.0f) ? 0u : (uint32_t)(nearest_int_magic(__fdiv_rn(__fadd_rn(v[j], bias), s)) & 0x0f);
-            csum += (int)c[j];
-        }
-        csum += __shfl_xor_sync(0xffffffffu, csum, 1);
-        csum += __shfl_xor_sync(0xffffffffu, csum, 2);
-        float smax = fmaxf(kTrueMin, s), bmax = fmaxf(kTrueMin, bias);
-#pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
-            smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-            bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-        }
-        const float ss = __fdiv_rn(smax, 63.0f), sbias = __fdiv_rn(bmax, 63.0f);
-        const int s6 = (ss == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(s, ss)) & 0x3f);
-        const int b6 = (sbias == 0.0f) ? 0 : (nearest_int_magic(__fdiv_rn(bias, sbias)) & 0x3f);
+        int csum, s6, b6;
+        float ss, sbias;
+        q4k_quantize_block(v, c, csum, ss, sbias, s6, b6);
         xe[b * 32 + lane] = c[0] | (c[2] << 8) | (c[4] << 16) | (c[6] << 24);
         xo[b * 32 + lane] = c[1] | (c[3] << 8) | (c[5] << 16) | (c[7] << 24);
         if ((lane & 3) == 0)
@@ -384,6 +394,90 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
         }
     }
     __syncthreads();
+}
+
+// quantize_tensor_q4k_in_situ (tensor.c:281-310) for whole tensors whose last dimension is a multiple of 256: every
+// 256-element block is independent, one warp per block, output in the reference's 160-byte block layout
+// {u32 tag=0x42, u32 len=256, u32 meta=0, f32 s_scale, f32 s_bias, u8 sb[12], u8 value[128]} (tensor.h:96-114).
+__global__ void __launch_bounds__(256) k_q4k_quantize_blocks(const float *__restrict__ x, unsigned long long nblocks, uint8_t *__restrict__ blocks) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (unsigned long long)gridDim.x * 8;
+    for (unsigned long long b = w0; b < nblocks; b += nw) {
+        float v[8];
+        const float4 *src = reinterpret_cast<const float4 *>(x + b * 256 + lane * 8);
+        const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+        v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        uint32_t c[8];
+        int csum, s6, b6;
+        float ss, sbias;
+        q4k_quantize_block(v, c, csum, ss, sbias, s6, b6);
+        uint32_t *blk = reinterpret_cast<uint32_t *>(blocks + b * 160);
+        blk[8 + lane] = (c[0] | (c[1] << 4)) | ((c[2] | (c[3] << 4)) << 8) | ((c[4] | (c[5] << 4)) << 16) | ((c[6] | (c[7] << 4)) << 24);
+        uint32_t sb0 = 0, sb1 = 0, sb2 = 0;       // tensor.c:198-241 packing of the eight 6-bit scale / bias codes
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t sl = (uint32_t)__shfl_sync(0xffffffffu, s6, 4 * g), sh = (uint32_t)__shfl_sync(0xffffffffu, s6, 4 * (g + 4));
+            const uint32_t bl = (uint32_t)__shfl_sync(0xffffffffu, b6, 4 * g), bh = (uint32_t)__shfl_sync(0xffffffffu, b6, 4 * (g + 4));
+            sb0 |= ((((sh & 0x30u) << 2) | (sl & 0x3fu)) & 0xffu) << (8 * g);
+            sb1 |= ((((bh & 0x30u) << 2) | (bl & 0x3fu)) & 0xffu) << (8 * g);
+            sb2 |= ((((bh & 0x0fu) << 4) | (sh & 0x0fu)) & 0xffu) << (8 * g);
+        }
+        if (lane == 0) {
+            blk[0] = 0x42u; blk[1] = 256u; blk[2] = 0u; blk[3] = __float_as_uint(ss); blk[4] = __float_as_uint(sbias);
+            blk[5] = sb0; blk[6] = sb1; blk[7] = sb2;
+        }
+    }
+}
+
+// matmul_q4k (tensor.c:438-471) on the reference's own block layout for BOTH operands (x already quantised by the caller):
+// one warp per row, lane = (block of the 4-block step, group); dot_two_blocks_q4k's integer sums with dp4a, its 4-term
+// fp32 expression left to right, groups then blocks accumulated in the reference's order.
+__global__ void __launch_bounds__(256) k_q4k_matvec_blocks(const uint8_t *__restrict__ wblocks, const uint8_t *__restrict__ xblocks,
+                                                           uint32_t rows, uint32_t bpr, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, gi = lane & 7, j = gi & 3;
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float acc = 0.0f;
+    for (uint32_t b0 = 0; b0 < bpr; b0 += 4) {
+        const uint32_t b = b0 + (lane >> 3);
+        const bool on = b < bpr;
+        float term = 0.0f;
+        if (on) {
+            const uint8_t *wb = wblocks + ((size_t)row * bpr + b) * 160, *xb = xblocks + (size_t)b * 160;
+            const uint32_t *wr = reinterpret_cast<const uint32_t *>(wb), *xr = reinterpret_cast<const uint32_t *>(xb);
+            auto group_sb = [&](const uint32_t *rec, float &s, float &bb) {       // get_group_scale_and_bias, tensor.c:113-141
+                const uint32_t bs = (rec[5] >> (8 * j)) & 0xff, bi = (rec[6] >> (8 * j)) & 0xff, bh = (rec[7] >> (8 * j)) & 0xff;
+                const uint32_t s6 = (gi < 4) ? (bs & 0x3f) : ((((bs >> 6) << 4) | (bh & 0x0f)) & 0x3f);
+                const uint32_t b6 = (gi < 4) ? (bi & 0x3f) : ((((bi >> 6) << 4) | (bh >> 4)) & 0x3f);
+                s = __fmul_rn((float)s6, __uint_as_float(rec[3])); bb = __fmul_rn((float)b6, __uint_as_float(rec[4]));
+            };
+            float sp, bp, sq, bq;
+            group_sb(wr, sp, bp); group_sb(xr, sq, bq);
+            int spq = 0, spp = 0, sqq = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int wv = (int)wr[8 + gi * 4 + t], xv = (int)xr[8 + gi * 4 + t];
+                const int wl = wv & 0x0f0f0f0f, wh = (wv >> 4) & 0x0f0f0f0f, xl = xv & 0x0f0f0f0f, xh = (xv >> 4) & 0x0f0f0f0f;
+                spq = __dp4a(wl, xl, spq); spq = __dp4a(wh, xh, spq);
+                spp = __dp4a(wl, 0x01010101, spp); spp = __dp4a(wh, 0x01010101, spp);
+                sqq = __dp4a(xl, 0x01010101, sqq); sqq = __dp4a(xh, 0x01010101, sqq);
+            }
+            term = __fmul_rn(__fmul_rn(sp, sq), (float)spq);                      // tensor.c:425-428, left to right
+            term = __fsub_rn(term, __fmul_rn(__fmul_rn(sp, bq), (float)spp));
+            term = __fsub_rn(term, __fmul_rn(__fmul_rn(sq, bp), (float)sqq));
+            term = __fadd_rn(term, __fmul_rn(__fmul_rn(32.0f, bp), bq));
+        }
+        float dot = 0.0f;
+        const int lead = lane & ~7;
+#pragma unroll
+        for (int g = 0; g < 8; g++) dot = __fadd_rn(dot, __shfl_sync(0xffffffffu, term, lead + g));
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            const float t = __shfl_sync(0xffffffffu, dot, bb * 8);
+            if (b0 + bb < bpr) acc = __fadd_rn(acc, t);
+        }
+    }
+    if (lane == 0) out[row] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ EXPORTS = [
     "nb200_write_x", "nb200_run_layer", "nb200_profile_tokens", "nb200_trace_token", "nb200_kernel_launches", "nb200_launches_per_token", "nb200_weight_bytes",
     "nb200_op_rmsnorm", "nb200_op_q80_quantize", "nb200_op_q80_matvec", "nb200_op_f32_matvec",
     "nb200_op_q4k_quantize", "nb200_op_q4k_matvec",
+    "nb200_op_q4k_quantize_blocks", "nb200_op_q4k_matvec_blocks",
     "nb200_engine_create_tp", "nb200_tp_export", "nb200_tp_attach_ipc", "nb200_tp_attach_local",
 ]
 
@@ -82,6 +83,8 @@ def lib():
         L.nb200_op_f32_matvec.argtypes = [f32p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.nb200_op_q4k_quantize.argtypes = [u8p, f32p, C.c_uint32]
         L.nb200_op_q4k_matvec.argtypes = [f32p, f32p, u8p, C.c_uint32, C.c_uint32]
+        L.nb200_op_q4k_quantize_blocks.argtypes = [u8p, f32p, C.c_uint64]
+        L.nb200_op_q4k_matvec_blocks.argtypes = [f32p, u8p, u8p, C.c_uint32, C.c_uint32]
         L.nb200_host_expf_ref.restype = C.c_float
         L.nb200_host_expf_ref.argtypes = [C.c_float]
         L.nb200_host_expf_ref_array.argtypes = [f32p, f32p, C.c_uint64]
@@ -322,6 +325,22 @@ def op_q4k_matvec(x, w_blocks, n, d):
     x = np.ascontiguousarray(x, np.float32); w_blocks = np.ascontiguousarray(w_blocks, np.uint8)
     out = np.empty(d, np.float32)
     _check(lib().nb200_op_q4k_matvec(_p(out, f32p), _p(x, f32p), _p(w_blocks, u8p), n, d))
+    return out
+
+
+def op_q4k_quantize_blocks(x):
+    """Whole tensor (size % 256 == 0) -> reference 160-byte blocks (quantize_tensor_q4k_in_situ)."""
+    x = np.ascontiguousarray(x, np.float32).reshape(-1)
+    blocks = np.zeros((x.size // 256) * 160, np.uint8)
+    _check(lib().nb200_op_q4k_quantize_blocks(_p(blocks, u8p), _p(x, f32p), x.size // 256))
+    return blocks
+
+
+def op_q4k_matvec_blocks(x_blocks, w_blocks, n, d):
+    """matmul_q4k with both operands already in the reference block layout."""
+    x_blocks = np.ascontiguousarray(x_blocks, np.uint8); w_blocks = np.ascontiguousarray(w_blocks, np.uint8)
+    out = np.empty(d, np.float32)
+    _check(lib().nb200_op_q4k_matvec_blocks(_p(out, f32p), _p(x_blocks, u8p), _p(w_blocks, u8p), n, d))
     return out
 
 

@@ -120,11 +120,38 @@ def test_q4k_matvec_bit_exact(n, d):
     assert_bits_equal(E.op_q4k_matvec(x, wb, n, d), want, "q4k matvec")
 
 
+@pytest.mark.parametrize("lines,n", [(1, 256), (7, 768), (300, 1024), (70000, 256)])
+def test_q4k_quantize_whole_tensor_bit_exact(lines, n):
+    """quantize_tensor_q4k_in_situ (tensor.c:281-310): every block of every line, incl. > one 64 Ki-block chunk."""
+    x = edgey(np.random.default_rng(lines + n), lines * n)
+    got = E.op_q4k_quantize_blocks(x)
+    want = np.zeros(got.size, np.uint8)
+    oracle().nor_q4k_quantize_rows(want.ctypes.data_as(ob.u8p), x.ctypes.data_as(ob.f32p), lines, n)
+    assert_bits_equal(got, want, "q4k tensor blocks")
+    if lines * n <= 1 << 16:
+        assert_bits_equal(got.reshape(-1, 160), mf.quantize_q4k_blocks(x.reshape(lines, n)).reshape(-1, 160), "vs the NumPy writer")
+
+
+@pytest.mark.parametrize("n,d", [(256, 5), (1024, 64), (2048, 130), (3072, 257), (768, 8), (2560, 33)])
+def test_q4k_matvec_prequantised_blocks_bit_exact(n, d):
+    """matmul_q4k (tensor.c:438-471) with x given as blocks, as the reference's own callers pass it."""
+    rng = np.random.default_rng(n * 3 + d)
+    x = edgey(rng, n)
+    W = (rng.standard_normal((d, n), dtype=np.float32) * np.float32(0.05)).astype(np.float32)
+    wb = mf.quantize_q4k_blocks(W).reshape(-1)
+    xb = o_q4k_quant(x)
+    want = np.zeros(d, np.float32)
+    oracle().nor_matvec_q4k(want.ctypes.data_as(ob.f32p), xb.ctypes.data_as(ob.u8p), wb.ctypes.data_as(ob.u8p), 0, d, n)
+    assert_bits_equal(E.op_q4k_matvec_blocks(xb, wb, n, d), want, "q4k matvec on blocks")
+
+
 def test_q4k_reference_kat():
     """infer/tools/export_q4k.c:394-450 recipe; outputs committed from the unmodified reference."""
     k = np.load(os.path.join(GOLDEN, "q4k_kat.npz"))
     assert_bits_equal(E.op_q4k_quantize(k["x"]), k["x_tensor"][44:], "activation")
     assert_bits_equal(E.op_q4k_matvec(k["x"], k["w_tensor"][44:], 768, 8), k["y"], "matmul_q4k")
+    assert_bits_equal(E.op_q4k_quantize_blocks(k["W"]), k["w_tensor"][44:], "weight tensor")
+    assert_bits_equal(E.op_q4k_matvec_blocks(k["x_tensor"][44:], k["w_tensor"][44:], 768, 8), k["y"], "matmul_q4k on blocks")
 
 
 @pytest.mark.parametrize("n,d", [(16, 32), (32, 80), (768, 100), (2048, 768)])

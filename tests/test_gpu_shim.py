@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, assert_bits_equal
 from nano_b200 import build as nb_build, modelfile as mf
 from oracle import bindings as ob
 
@@ -137,3 +137,41 @@ def test_nano_cli_binary_starts_and_reports_missing_model():
     r = subprocess.run([nb_build.NANO_CLI], input=b"", capture_output=True, timeout=60)
     assert r.returncode != 0
     assert b"open" in r.stderr.lower() or b"couldn" in r.stderr.lower()
+
+
+def test_q4k_tensor_functions_through_reference_names():
+    """tensor.h:160-166 as the reference's tools/export_q4k.c calls them (quantize_tensor_q4k -> matmul_q4k on a 3-D
+    weight with a layer index), against the outputs committed from the unmodified reference and the oracle."""
+    L = shim()
+    L.quantize_tensor_q4k.restype = C.c_void_p
+    L.quantize_tensor_q4k.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32)]
+    L.bytes_num_of_q4k_tensor.restype = C.c_uint64
+    L.bytes_num_of_q4k_tensor.argtypes = [C.c_void_p]
+    L.matmul_q4k.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_uint32]
+    f32p = C.POINTER(C.c_float)
+    k = np.load(os.path.join(GOLDEN, "q4k_kat.npz"))
+
+    def qt(arr, shape):
+        a = np.ascontiguousarray(arr, np.float32)
+        sh = (C.c_uint32 * len(shape))(*shape)
+        T = L.quantize_tensor_q4k(a.ctypes.data_as(f32p), len(shape), sh)
+        n = L.bytes_num_of_q4k_tensor(T)
+        return T, np.frombuffer(C.string_at(T, n), np.uint8).copy()
+
+    xT, xb = qt(k["x"], [768])
+    wT, wb = qt(k["W"], [8, 768])
+    assert_bits_equal(xb, k["x_tensor"], "x tensor image"); assert_bits_equal(wb, k["w_tensor"], "w tensor image")
+    y = np.zeros(8, np.float32)
+    L.matmul_q4k(y.ctypes.data_as(f32p), xT, wT, 0)
+    assert_bits_equal(y, k["y"], "matmul_q4k")
+    # 3-D weight, layer slice 1 (tensor.c:452-461)
+    rng = np.random.default_rng(5)
+    W3 = (rng.standard_normal((3, 10, 512), dtype=np.float32) * np.float32(0.05)).astype(np.float32)
+    x = rng.standard_normal(512, dtype=np.float32)
+    w3T, _ = qt(W3, [3, 10, 512]); x2T, x2b = qt(x, [512])
+    y3 = np.zeros(10, np.float32)
+    L.matmul_q4k(y3.ctypes.data_as(f32p), x2T, w3T, 1)
+    want = np.zeros(10, np.float32)
+    wblk = mf.quantize_q4k_blocks(W3[1]).reshape(-1)
+    ob.NanoOracle.lib().nor_matvec_q4k(want.ctypes.data_as(ob.f32p), x2b[44:].ctypes.data_as(ob.u8p), wblk.ctypes.data_as(ob.u8p), 0, 10, 512)
+    assert_bits_equal(y3, want, "matmul_q4k layer 1")
