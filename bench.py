@@ -385,9 +385,18 @@ def main():
         # per_kernel keeps the phase-by-phase profile of the same device code run as separate launches.
         kname = "k_decode_cluster" if eng.path.startswith("cluster") else "k_decode_mega"
         launch_us = dec_ms / args.steps * 1e3
+        ptraffic = None
+        try:
+            ptraffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(
+                args.workload + (":cluster" if kname.endswith("cluster") else ":mega"))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": f"{kname} (one launch decodes {n_dec} tokens: all layers + classifier + argmax)",
-                "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None,
-                "traffic_source": None, "peak_source": peak_src, "alg_bytes_per_launch": bytes_tok * n_dec,
+                "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
+                "traffic": ptraffic * n_dec if ptraffic else None,
+                "traffic_source": (f"ncu --set full capture of one {kname} launch, per-token bytes x {n_dec} tokens, profiles/r1_ncu_full_"
+                                   + ("cluster" if kname.endswith("cluster") else "megakernel") + ".md") if ptraffic else None,
+                "peak_source": peak_src, "alg_bytes_per_launch": bytes_tok * n_dec,
                 "mean_launch_us": launch_us, "share_of_step": 1.0,
                 "phase_profile_note": "per_kernel = the same phase code launched as separate kernels (graph/PDL off), CUDA events per launch",
                 "per_kernel": per_class}

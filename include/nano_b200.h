@@ -134,6 +134,7 @@ int nb200_run_layer(nb200_engine *e, uint32_t layer, uint32_t pos, uint32_t is_c
  * 0 embed, 1 qkv, 2 attention, 3 o-proj, 4 w1|w3, 5 w2, 6 classifier. Used by bench.py's roofline. */
 int nb200_profile_tokens(nb200_engine *e, const uint32_t *ids, uint32_t start, uint32_t n, float ms[7], uint32_t counts[7]);
 /* debug: clock64() stamps of CTA 0 after every grid barrier of one token in the persistent kernel */
+int nb200_read_attn_trace(nb200_engine *e, unsigned long long *stamps32);   /* debug, NB200_ATTN_DBG=1 */
 int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned long long *stamps, uint32_t cap, uint32_t *count);
 uint64_t nb200_kernel_launches(const nb200_engine *e);      /* cumulative kernel launches issued */
 uint32_t nb200_launches_per_token(const nb200_engine *e);

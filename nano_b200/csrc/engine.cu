@@ -112,6 +112,7 @@ struct nb200_engine {
     // tensor parallel (kernels.cuh "Tensor parallelism"): exchange block = [TpHdr | x | xba | hb]; d holds the LOCAL head counts
     uint32_t tp_rank = 0, tp_size = 1;
     bool tied = false;
+    unsigned long long *attn_dbg = nullptr;          // NB200_ATTN_DBG=1: %globaltimer stamps of layer L/2's attention kernel
     uint32_t g_H = 0, g_KV = 0, g_q_dim = 0, g_kv_dim = 0;     // whole-model values (== d.* on one GPU)
     unsigned char *tp_block = nullptr; size_t tp_block_bytes = 0;
     uint32_t tp_off_x = 0, tp_off_xba = 0, tp_off_hb = 0;
@@ -167,6 +168,7 @@ template <int QUANT, int EPI, bool TP>
 MatvecKern pick_matvec(int rb, int lpg) {
     if (QUANT == 0x80) {
 #define NB_PICK(RB_, L_) if (rb == RB_ && lpg == L_) return k_matvec<QUANT, EPI, RB_, L_, TP>;
+        if constexpr (EPI != EPI_SWIGLU) { NB_PICK(1, 2) NB_PICK(1, 4) NB_PICK(1, 8) NB_PICK(1, 16) }      // SwiGLU pairs rows: RB even
         NB_PICK(2, 2) NB_PICK(2, 4) NB_PICK(2, 8) NB_PICK(2, 16)
         NB_PICK(4, 2) NB_PICK(4, 4) NB_PICK(4, 8) NB_PICK(4, 16)
 #undef NB_PICK
@@ -218,6 +220,8 @@ int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, 
     }
     const uint32_t total_warps = (uint32_t)num_sms * grid_mult() * kWarps;
     int rb = (m.rows >= total_warps * 8) ? 4 : 2;
+    // few long rows (O / W2 of the larger models): one row per warp keeps every warp busy, 4 tiles in flight each
+    if (d.quant == 0x80u && epi != EPI_SWIGLU && m.rows <= total_warps && m.n >= 2048 && !getenv("NB200_NO_RB1")) rb = 1;
     const int lpg = (d.quant == 0x80u) ? (int)(d.gs / 16) : 8;
     MatvecKern k = nullptr;
     const bool tp = a.tp.size > 1;
@@ -283,6 +287,7 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.xba = e->xba;
         a.ws_m = e->ws_m; a.ws_l = e->ws_l; a.ws_acc = e->ws_acc; a.ticket = e->tickets;
         a.st = e->st; a.nsplit_max = e->nsplit_max; a.chunk_cap = e->chunk_cap; a.d = d;
+        a.dbg = (l == d.L / 2) ? e->attn_dbg : nullptr;
         void (*kern)(const AttnArgs) = k_attention;
         uint32_t smem = e->attn_smem;
         const bool tp = e->tp_size > 1;
@@ -903,6 +908,7 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     DM(e->st, sizeof(DevState)); CK(cudaMemset(e->st, 0, sizeof(DevState)));
     const size_t maxn = F > QD ? (F > E ? F : E) : (QD > E ? QD : E);
     DM(e->dump_codes, maxn * 2 + 64); DM(e->dump_scales, maxn * 4 + 64);
+    if (getenv("NB200_ATTN_DBG")) { DM(e->attn_dbg, 32 * 8); CK(cudaMemset(e->attn_dbg, 0, 32 * 8)); }
     CK(cudaHostAlloc(&e->st_host, sizeof(DevState), cudaHostAllocDefault));
     CK(cudaHostAlloc(&e->tok_host, 64, cudaHostAllocDefault));
     memset(e->st_host, 0, sizeof(DevState));
@@ -1224,6 +1230,15 @@ int nb200_profile_tokens(nb200_engine *e, const uint32_t *ids, uint32_t start, u
     }
     e->prof.clear();
     return r;
+}
+
+// Debug (NB200_ATTN_DBG=1 at engine creation): the 32 %globaltimer stamps (ns) of the last run of layer L/2's attention kernel.
+int nb200_read_attn_trace(nb200_engine *e, unsigned long long *stamps32) {
+    if (!e || !stamps32 || !e->attn_dbg) return fail(NB200_EINVAL, "attention trace not enabled (NB200_ATTN_DBG=1)");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(stamps32, e->attn_dbg, 32 * 8, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 // Debug: per-barrier clock64() stamps of CTA 0 for one token through the persistent kernel (5L+3 stamps + 1).

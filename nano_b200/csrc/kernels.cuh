@@ -194,20 +194,69 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // CTAs (another kernel, or another phase of the persistent kernel), so it must not come from L1 / the
 // non-coherent path.
 // LL (tensor parallel): src is a vector of {value, epoch} words; spin per element until exchange tp->wait_ph has landed.
-template <int NT, bool LL = false>
+// SB = loads in flight per thread: 1 keeps the register footprint of the persistent kernels, 4 (x float4) is what
+// the stand-alone matvec kernels use.
+template <int NT, bool LL = false, int SB = 1>
 __device__ __forceinline__ void stage_vector(const float *src, const float *__restrict__ gain, int n, float *stage, const TpArgs *tp = nullptr) {
     float *gstage = stage + n;                       // the rmsnorm gain rides along (one L2 latency, not two)
-    uint32_t need = 0;
-    if (LL && tp->wait_ph) need = tp_epoch(*tp, tp->wait_ph);
-    for (int i = threadIdx.x; i < n; i += NT) {
-        float v;
-        if (LL) {
-            const unsigned long long *e = reinterpret_cast<const unsigned long long *>(src) + i;
-            v = __uint_as_float(tp->wait_ph ? tp_spin_load(*tp, e, need) : (uint32_t)__ldcg(e));
-        } else v = __ldcg(src + i);
-        const float g = gain ? __ldg(gain + i) : 0.0f;
-        stage[i] = v;
-        if (gain) gstage[i] = g;
+    if (!LL && SB == 1) {
+        for (int i = threadIdx.x; i < n; i += NT) {
+            const float v = __ldcg(src + i);
+            const float g = gain ? __ldg(gain + i) : 0.0f;
+            stage[i] = v;
+            if (gain) gstage[i] = g;
+        }
+        __syncthreads();
+        return;
+    }
+    // Every load of a batch is issued before any result is used: a thread's share of a long vector (19 elements of
+    // n = 9728 with 512 threads) costs a few L2 round trips instead of one per element.
+    if (LL) {
+        uint32_t need = 0;
+        if (tp->wait_ph) need = tp_epoch(*tp, tp->wait_ph);
+        const unsigned long long *e = reinterpret_cast<const unsigned long long *>(src);
+        constexpr int B = 8;
+        for (int i0 = threadIdx.x; i0 < n; i0 += NT * B) {
+            unsigned long long w[B]; float g[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int i = i0 + u * NT;
+                if (i < n) { w[u] = ld_relaxed_sys_u64(e + i); g[u] = gain ? __ldg(gain + i) : 0.0f; }
+            }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int i = i0 + u * NT;
+                if (i < n) {
+                    uint32_t bits = (uint32_t)w[u];
+                    if (tp->wait_ph && (int32_t)((uint32_t)(w[u] >> 32) - need) < 0) bits = tp_spin_load(*tp, e + i, need);
+                    stage[i] = __uint_as_float(bits);
+                    if (gain) gstage[i] = g[u];
+                }
+            }
+        }
+    } else {
+        constexpr int B = 4;                         // x 4 floats per load
+        const bool vec = ((n & 3) == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(gain)) & 15) == 0);
+        const int n4 = vec ? (n >> 2) : 0;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        const float4 *g4 = reinterpret_cast<const float4 *>(gain);
+        for (int i0 = threadIdx.x; i0 < n4; i0 += NT * B) {
+            float4 v[B], g[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int i = i0 + u * NT;
+                if (i < n4) { v[u] = __ldcg(s4 + i); if (gain) g[u] = __ldg(g4 + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int i = i0 + u * NT;
+                if (i < n4) { reinterpret_cast<float4 *>(stage)[i] = v[u]; if (gain) reinterpret_cast<float4 *>(gstage)[i] = g[u]; }
+            }
+        }
+        for (int i = (n4 << 2) + threadIdx.x; i < n; i += NT) {      // unaligned / n % 4 != 0 callers (op-level entry points only)
+            stage[i] = __ldcg(src + i);
+            if (gain) gstage[i] = __ldg(gain + i);
+        }
     }
     __syncthreads();
 }
@@ -258,10 +307,10 @@ __host__ __device__ inline uint32_t act_smem_bytes(uint32_t quant, uint32_t n, u
     return act_region_bytes(quant, n, gs) + 2u * n * 4u;      // + staging copies of the source and the gain
 }
 
-template <int NT, bool LL = false>
+template <int NT, bool LL = false, int SB = 1>
 __device__ void prep_f32(const float *src, const float *__restrict__ gain, int n, bool exact, float *act, float *stage, float *red,
                          const TpArgs *tp = nullptr) {
-    stage_vector<NT, LL>(src, gain, n, stage, tp);
+    stage_vector<NT, LL, SB>(src, gain, n, stage, tp);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     for (int i = threadIdx.x; i < n; i += NT) act[i] = act_value(stage, n, gain != nullptr, inv, i);
@@ -280,13 +329,13 @@ __device__ __forceinline__ int q80_code(float v, float sc, float rinv) {
 }
 
 // tensor.c:21-46 (division and round-half-away exactly as the strict reference; zero group -> 0)
-template <int NT, bool LL = false>
+template <int NT, bool LL = false, int SB = 1>
 __device__ void prep_q80(const float *src, const float *__restrict__ gain, int n, int gs, bool exact,
                          unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales,
                          unsigned long long *dbg = nullptr, const TpArgs *tp = nullptr) {
     int8_t *codes = reinterpret_cast<int8_t *>(act);
     float *scales = reinterpret_cast<float *>(act + ((n + 15) & ~15));
-    stage_vector<NT, LL>(src, gain, n, stage, tp);
+    stage_vector<NT, LL, SB>(src, gain, n, stage, tp);
     NB_STAMP(dbg, 2);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
@@ -358,13 +407,13 @@ __device__ __forceinline__ void q4k_quantize_block(const float (&v)[8], uint32_t
 //   dump_scales[0..n/256)      = ss
 //   dump_scales[n/256..2n/256) = sbias
 //   dump_codes[n .. n + n/32)  = s6, dump_codes[n + n/32 .. n + 2n/32) = b6
-template <int NT, bool LL = false>
+template <int NT, bool LL = false, int SB = 1>
 __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n, bool exact,
                          unsigned char *act, float *stage, float *red, int8_t *dump_codes, float *dump_scales, const TpArgs *tp = nullptr) {
     uint32_t *xe = reinterpret_cast<uint32_t *>(act);
     uint32_t *xo = reinterpret_cast<uint32_t *>(act + n / 2);
     float4 *gp = reinterpret_cast<float4 *>(act + n);
-    stage_vector<NT, LL>(src, gain, n, stage, tp);
+    stage_vector<NT, LL, SB>(src, gain, n, stage, tp);
     float inv = 1.0f;
     if (gain) inv = rms_inverse<NT>(stage, n, exact, red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -698,7 +747,9 @@ __device__ __forceinline__ void prefetch_row_blocks(const void *w, uint32_t rows
     if (gain && warp == 0) for (uint32_t off = (cta * 32u + lane) * 32u; off < n; off += ncta * 32u * 32u) prefetch_l2(gain + off);
 }
 
-template <int QUANT, int EPI, int RB, int LPG, bool TP = false>
+// D (Q80 only) = weight tiles a warp keeps in flight along K: tile d+D of a row block is requested as soon as tile d has
+// been consumed, and the first D tiles are requested before the activation prologue.
+template <int QUANT, int EPI, int RB, int LPG, bool TP = false, int D = 1, int SB = 1>
 __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, uint32_t ncta, unsigned char *act, MatvecSmem &ms) {
     const Dims &d = a.d;
     // tensor parallel: local row r is element rbase + r of the (replicated) output vector; QKV outputs stay local
@@ -712,11 +763,15 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
 
     NB_STAMP(a.dbg, 0);
     // request this warp's first weight tile (and the residual it will add to) before the activation prologue
-    Q80Tile<RB> pre;
+    Q80Tile<RB> pre[D];
     float xres[RB];
     const bool has_first = gwarp < nblocks;
-    if (QUANT == 0x80 && has_first)
-        q80_load<RB, LPG>(pre, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), gwarp * RB, a.rows, a.n, 0);
+    if (QUANT == 0x80 && has_first) {
+#pragma unroll
+        for (int dd = 0; dd < D; dd++)
+            if (dd == 0 || dd * 1024u < a.n)
+                q80_load<RB, LPG>(pre[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), gwarp * RB, a.rows, a.n, dd * 1024u);
+    }
     if (EPI == EPI_RESID && has_first) {
 #pragma unroll
         for (int r = 0; r < RB; r++) {
@@ -725,9 +780,9 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
         }
     }
 
-    if (QUANT == 0x00) prep_f32<kThreads, TP>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red, &a.tp);
-    else if (QUANT == 0x80) { NB_STAMP(a.dbg, 1); prep_q80<kThreads, TP>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, a.dbg, &a.tp); }
-    else prep_q4k<kThreads, TP>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, &a.tp);
+    if (QUANT == 0x00) prep_f32<kThreads, TP, SB>(a.src, a.gain, a.n, exact, reinterpret_cast<float *>(act), stage, ms.red, &a.tp);
+    else if (QUANT == 0x80) { NB_STAMP(a.dbg, 1); prep_q80<kThreads, TP, SB>(a.src, a.gain, a.n, LPG * 16, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, a.dbg, &a.tp); }
+    else prep_q4k<kThreads, TP, SB>(a.src, a.gain, a.n, exact, act, stage, ms.red, cta == 0 ? a.dump_codes : nullptr, a.dump_scales, &a.tp);
     uint32_t out_epoch = 0;
     if (TP && a.tp.signal_ph) out_epoch = tp_epoch(a.tp, a.tp.signal_ph);
 
@@ -748,11 +803,23 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
         else if (QUANT == 0x80) {
 #pragma unroll
             for (int r = 0; r < RB; r++) val[r] = 0.0f;
-            if (kFirst) q80_consume<RB, LPG>(pre, a.n, 0, act, val);
-            for (uint32_t k0 = kFirst ? 1024u : 0u; k0 < a.n; k0 += 1024) {
-                Q80Tile<RB> t;
-                q80_load<RB, LPG>(t, static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, k0);
-                q80_consume<RB, LPG>(t, a.n, k0, act, val);
+            Q80Tile<RB> t[D];
+#pragma unroll
+            for (int dd = 0; dd < D; dd++) {
+                if (kFirst) t[dd] = pre[dd];
+                else if (dd == 0 || dd * 1024u < a.n)
+                    q80_load<RB, LPG>(t[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, dd * 1024u);
+            }
+            for (uint32_t k0 = 0; k0 < a.n; k0 += D * 1024u) {
+#pragma unroll
+                for (int dd = 0; dd < D; dd++) {
+                    const uint32_t k = k0 + dd * 1024u;
+                    if (dd == 0 || k < a.n) {
+                        q80_consume<RB, LPG>(t[dd], a.n, k, act, val);       // K ascending: the reference's group order
+                        if (k + D * 1024u < a.n)
+                            q80_load<RB, LPG>(t[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, k + D * 1024u);
+                    }
+                }
             }
         } else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
 
@@ -879,12 +946,13 @@ __device__ __forceinline__ uint32_t cls_finalize(const MatvecArgs &a, uint32_t n
 
 template <int QUANT, int EPI, int RB, int LPG, bool TP = false>
 __global__ void __launch_bounds__(kThreads, 1) k_matvec(const MatvecArgs a) {
+    constexpr int D = (QUANT != 0x80) ? 1 : (RB == 1) ? 4 : (RB == 2) ? 2 : 1;     // ~4 KB of weights in flight per warp
     extern __shared__ __align__(16) unsigned char act[];
     __shared__ MatvecSmem ms;
     pdl_launch_dependents();
     prefetch_row_blocks<QUANT, RB>(a.w, a.rows, a.n, blockIdx.x, gridDim.x, 4);
     pdl_wait();
-    matvec_phase<QUANT, EPI, RB, LPG, TP>(a, blockIdx.x, gridDim.x, act, ms);
+    matvec_phase<QUANT, EPI, RB, LPG, TP, D, 4>(a, blockIdx.x, gridDim.x, act, ms);
 
     if (EPI == EPI_CLS) {
         if (threadIdx.x == 0) {
@@ -992,7 +1060,10 @@ struct AttnArgs {
     uint32_t nsplit_max, chunk_cap;
     Dims d;
     TpArgs tp;               // tensor parallel: xba is pushed to every rank (k_attention_fast<KVM, true>)
+    unsigned long long *dbg; // optional %globaltimer stamps of kv head 0 (tools/gpu_attn_trace.py): [0..9] split 0, [16..21] merging CTA
 };
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define AG_STAMP(cond, k) do { if (a.dbg && (cond) && threadIdx.x == 0) a.dbg[k] = gtime(); } while (0)
 
 // one head vector: optional rmsnorm (Qwen3) + rope; in/out in shared memory; called by one warp
 __device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict__ gain, const float *__restrict__ cr,
@@ -1046,12 +1117,29 @@ __device__ __forceinline__ void head_norm_rope(float *h, const float *__restrict
 __host__ __device__ inline uint32_t attn_stream_ws_floats(uint32_t kvm, uint32_t hd, uint32_t nwarps) { return nwarps * kvm * (hd + 4u) + kvm * (hd + 2u) + 16u; }
 __host__ __device__ inline uint32_t attn_fast_smem_floats(uint32_t kvm, uint32_t hd, uint32_t chunk_cap, uint32_t nsplit_max, uint32_t nwarps) {
     (void)chunk_cap;
-    return attn_stream_ws_floats(kvm, hd, nwarps) + kvm * nsplit_max + 2u * kvm + 16u;
+    uint32_t ws = attn_stream_ws_floats(kvm, hd, nwarps);
+    const uint32_t merge = nsplit_max * kvm * hd;          // the merge stages all partial accumulators of a kv head over the workspace
+    if (merge > ws) ws = merge;
+    return ws + kvm * nsplit_max + 2u * kvm + 16u;
 }
 
-// head-norm (Qwen3) + RoPE of the float4 slice a lane holds of one head vector (infer.c:814-835); lpr lanes = one vector
-__device__ __forceinline__ float4 norm_rope_slice(float4 v, const float *__restrict__ gain, const float *__restrict__ cr, const float *__restrict__ ci,
-                                                  const Dims &d, uint32_t lpr, uint32_t col, bool colon) {
+// head-norm (Qwen3) + RoPE of the float4 slice a lane holds of one head vector (infer.c:814-835); lpr lanes = one vector.
+// The same arithmetic with the position's RoPE entries (and the head-norm gain) already in registers, so their loads can be
+// issued together with the q / K / V loads instead of after the norm's shuffles.
+struct RopeTab { float4 c, sn; };      // arch 3: cos/sin of the lane's 4 pair indices; otherwise {c0, s0, c1, s1} in c
+__device__ __forceinline__ RopeTab rope_tab_load(const float *__restrict__ cr, const float *__restrict__ ci, const Dims &d, uint32_t col, bool colon) {
+    RopeTab t; t.c = make_float4(0, 0, 0, 0); t.sn = make_float4(0, 0, 0, 0);
+    if (colon) {
+        if (d.arch == 3u) {
+            const uint32_t half = d.hd / 2, i0 = (col < half) ? col : col - half;
+            t.c = *reinterpret_cast<const float4 *>(cr + i0); t.sn = *reinterpret_cast<const float4 *>(ci + i0);
+        } else {
+            t.c = make_float4(cr[col / 2], ci[col / 2], cr[col / 2 + 1], ci[col / 2 + 1]);
+        }
+    }
+    return t;
+}
+__device__ __forceinline__ float4 norm_rope_apply(float4 v, float4 gn, const RopeTab &rt, const Dims &d, uint32_t lpr, uint32_t col, bool colon) {
     if (d.arch == 3u) {
         float ss = colon ? fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))) : 0.0f;
         for (uint32_t o = lpr >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -1059,29 +1147,25 @@ __device__ __forceinline__ float4 norm_rope_slice(float4 v, const float *__restr
         ss = __fadd_rn(ss, 1e-5f);
         const float inv = __fdiv_rn(1.0f, __fsqrt_rn(ss));
         if (colon) {
-            const float4 gn = *reinterpret_cast<const float4 *>(gain + col);
             v.x = __fmul_rn(gn.x, __fmul_rn(inv, v.x)); v.y = __fmul_rn(gn.y, __fmul_rn(inv, v.y));
             v.z = __fmul_rn(gn.z, __fmul_rn(inv, v.z)); v.w = __fmul_rn(gn.w, __fmul_rn(inv, v.w));
         }
-        // half-split pairs (i, i + hd/2): the partner element lives lpr/2 lanes away (hd == 4*lpr on this path)
         const uint32_t half = d.hd / 2, hl = lpr >> 1;
         float4 o4;
         o4.x = __shfl_xor_sync(0xffffffffu, v.x, hl); o4.y = __shfl_xor_sync(0xffffffffu, v.y, hl);
         o4.z = __shfl_xor_sync(0xffffffffu, v.z, hl); o4.w = __shfl_xor_sync(0xffffffffu, v.w, hl);
         if (colon) {
-            const bool first = col < half;
-            const uint32_t i0 = first ? col : col - half;
-            const float4 c = *reinterpret_cast<const float4 *>(cr + i0), sn = *reinterpret_cast<const float4 *>(ci + i0);
-            if (first) {      // head[i] = v0*c - v1*s
+            const float4 c = rt.c, sn = rt.sn;
+            if (col < half) {
                 v.x = __fsub_rn(__fmul_rn(v.x, c.x), __fmul_rn(o4.x, sn.x)); v.y = __fsub_rn(__fmul_rn(v.y, c.y), __fmul_rn(o4.y, sn.y));
                 v.z = __fsub_rn(__fmul_rn(v.z, c.z), __fmul_rn(o4.z, sn.z)); v.w = __fsub_rn(__fmul_rn(v.w, c.w), __fmul_rn(o4.w, sn.w));
-            } else {          // head[i + half] = v1*c + v0*s
+            } else {
                 v.x = __fadd_rn(__fmul_rn(v.x, c.x), __fmul_rn(o4.x, sn.x)); v.y = __fadd_rn(__fmul_rn(v.y, c.y), __fmul_rn(o4.y, sn.y));
                 v.z = __fadd_rn(__fmul_rn(v.z, c.z), __fmul_rn(o4.z, sn.z)); v.w = __fadd_rn(__fmul_rn(v.w, c.w), __fmul_rn(o4.w, sn.w));
             }
         }
-    } else if (colon) {        // adjacent pairs (2i, 2i+1): both pairs of the float4 are lane-local (infer.c:681-690)
-        const float c0 = cr[col / 2], s0 = ci[col / 2], c1 = cr[col / 2 + 1], s1 = ci[col / 2 + 1];
+    } else if (colon) {
+        const float c0 = rt.c.x, s0 = rt.c.y, c1 = rt.c.z, s1 = rt.c.w;
         const float x = v.x, y = v.y, z = v.z, w = v.w;
         v.x = __fsub_rn(__fmul_rn(x, c0), __fmul_rn(y, s0)); v.y = __fadd_rn(__fmul_rn(x, s0), __fmul_rn(y, c0));
         v.z = __fsub_rn(__fmul_rn(z, c1), __fmul_rn(w, s1)); v.w = __fadd_rn(__fmul_rn(z, s1), __fmul_rn(w, c1));
@@ -1106,21 +1190,28 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
     const bool colon = col < hd;
     const float inv_dv = 1.0f / sqrtf((float)hd);   // fast mode: score * (1/sqrt(hd)) and __expf; exact mode has its own kernel
 
+    // Everything that does not depend on other loads is requested first: q, the position's RoPE entries, the head-norm
+    // gain, and the warp's first batch of cache rows.  (One memory round trip instead of three or four in sequence.)
+    const uint32_t stride = NW * rpw;
     float4 qv[KVM];
 #pragma unroll
     for (int m = 0; m < KVM; m++) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (colon) v = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(q_src + m * hd + col)) : *reinterpret_cast<const float4 *>(q_src + m * hd + col);
-        qv[m] = norm_rope_slice(v, qn, cr, ci, d, lpr, col, colon);
+        qv[m] = make_float4(0, 0, 0, 0);
+        if (colon) qv[m] = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(q_src + m * hd + col)) : *reinterpret_cast<const float4 *>(q_src + m * hd + col);
     }
-    float mx[KVM], ls[KVM]; float4 av[KVM];
-#pragma unroll
-    for (int m = 0; m < KVM; m++) { mx[m] = -FLT_MAX; ls[m] = 0.0f; av[m] = make_float4(0, 0, 0, 0); }
-    AT_STAMP(1);
-
-    const uint32_t stride = NW * rpw;
-    for (uint32_t tb0 = warp * rpw; tb0 < len; tb0 += stride * U) {
-        float4 kr[U], vr[U];
+    const RopeTab rt = rope_tab_load(cr, ci, d, col, colon);
+    float4 gq = make_float4(0, 0, 0, 0);
+    if (d.arch == 3u && colon) gq = *reinterpret_cast<const float4 *>(qn + col);
+    // the current position's raw k / v rows and the k gain (used by the one warp whose batch contains `pos`: the split
+    // that holds it is on every kv head's critical path)
+    float4 kk0 = make_float4(0, 0, 0, 0), vv0 = make_float4(0, 0, 0, 0), gk = make_float4(0, 0, 0, 0);
+    if (colon && t0 + len > pos) {
+        kk0 = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(kraw_src + col)) : *reinterpret_cast<const float4 *>(kraw_src + col);
+        vv0 = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(vrow_src + col)) : *reinterpret_cast<const float4 *>(vrow_src + col);
+        if (d.arch == 3u) gk = *reinterpret_cast<const float4 *>(kn + col);
+    }
+    float4 kr[U], vr[U];
+    auto request_batch = [&](uint32_t tb0) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t tl = tb0 + u * stride + sub, t = t0 + tl;
@@ -1130,6 +1221,17 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
                 vr[u] = __ldcg(reinterpret_cast<const float4 *>(vbase + (size_t)t * hd + col));
             }
         }
+    };
+    uint32_t tb0 = warp * rpw;
+    if (tb0 < len) request_batch(tb0);
+#pragma unroll
+    for (int m = 0; m < KVM; m++) qv[m] = norm_rope_apply(qv[m], gq, rt, d, lpr, col, colon);
+    float mx[KVM], ls[KVM]; float4 av[KVM];
+#pragma unroll
+    for (int m = 0; m < KVM; m++) { mx[m] = -FLT_MAX; ls[m] = 0.0f; av[m] = make_float4(0, 0, 0, 0); }
+    AT_STAMP(1);
+
+    while (tb0 < len) {
         // scores of the whole batch first (independent shuffle-reductions), then ONE rescale of the running state
         float scr[U][KVM];
         bool vld[U];
@@ -1140,13 +1242,11 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
             // the current position's row: k is normalised + roped here (and stored for later tokens), v comes from the step's own output
             if (__any_sync(0xffffffffu, vld[u] && t == pos)) {
                 const bool mine = vld[u] && t == pos;
-                float4 kk = make_float4(0, 0, 0, 0);
-                if (mine && colon) kk = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(kraw_src + col)) : *reinterpret_cast<const float4 *>(kraw_src + col);
-                kk = norm_rope_slice(kk, kn, cr, ci, d, lpr, col, colon);      // executed by the whole warp (shuffles); only `mine` keeps it
+                const float4 kk = norm_rope_apply(kk0, gk, rt, d, lpr, col, colon);      // executed by the whole warp (shuffles); only `mine` keeps it
                 if (mine && colon) {
                     kr[u] = kk;
                     *reinterpret_cast<float4 *>(kbase + (size_t)pos * hd + col) = kk;
-                    vr[u] = SRC_GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(vrow_src + col)) : *reinterpret_cast<const float4 *>(vrow_src + col);
+                    vr[u] = vv0;
                 }
             }
 #pragma unroll
@@ -1174,6 +1274,8 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
             }
             ls[m] = l2; av[m] = a4; mx[m] = mn;
         }
+        tb0 += stride * U;
+        if (tb0 < len) request_batch(tb0);
     }
     AT_STAMP(2);
     // merge the row slots of a warp
@@ -1241,13 +1343,18 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
     const uint32_t t0 = split * chunk, t1 = min(range, t0 + chunk), len = t1 - t0;
     float *ws = sm;
     float *outp = ws + (size_t)NW * KVM * (hd + 4);
-    float *wsc = outp + KVM * (hd + 2);
+    uint32_t region = NW * KVM * (hd + 4) + KVM * (hd + 2);           // the merge's staging area may be larger (attn_fast_smem_floats)
+    if (a.nsplit_max * KVM * hd > region) region = a.nsplit_max * KVM * hd;
+    float *wsc = sm + region;
     float *stat = wsc + KVM * a.nsplit_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *cr = a.rope_cos + (size_t)pos * (hd / 2), *ci = a.rope_sin + (size_t)pos * (hd / 2);
     float *kbase = a.kc + (size_t)g * d.max_seq * hd, *vbase = a.vc + (size_t)g * d.max_seq * hd;
+    const bool tr = (g == 0 && split == 0);
+    AG_STAMP(tr, 2);
     attn_stream_partial<KVM, NT, true>(d, a.q + (size_t)g * KVM * hd, a.kraw + (size_t)g * hd, vbase + (size_t)pos * hd, kbase, vbase,
                                        a.qnorm, a.knorm, cr, ci, pos, t0, len, ws, outp);
+    AG_STAMP(tr, 3);
     for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
         a.ws_acc[((size_t)(g * KVM + m) * a.nsplit_max + split) * hd + i] = outp[m * (hd + 2) + i];
@@ -1257,42 +1364,72 @@ __device__ __forceinline__ void attn_item(const AttnArgs &a, uint32_t g, uint32_
         a.ws_m[slot] = outp[threadIdx.x * (hd + 2) + hd]; a.ws_l[slot] = outp[threadIdx.x * (hd + 2) + hd + 1];
     }
     __syncthreads();
+    AG_STAMP(tr, 4);
     if (threadIdx.x == 0) {
         __threadfence();
         const uint32_t t = atomicAdd(a.ticket + g, 1u);
         is_last = (t == nsplit - 1) ? 1u : 0u;
     }
     __syncthreads();
+    AG_STAMP(tr, 5);
     if (!is_last) return;      // uniform across the CTA
     __threadfence();
-    // ---- merge: warp m computes exp(m_s - M) / L for its head; then all threads combine ----
+    AG_STAMP(g == 0, 16);
+    // ---- merge.  Every load of the partials is issued before any is consumed (one L2 round trip instead of one per
+    // unrolled group): the accumulators go to shared memory `macc` (it reuses the streaming workspace), the per-split
+    // maxima / sums to registers; then warp m computes exp(m_s - M) and L for its head, and all threads combine in the
+    // fixed split order. ----
+    float *macc = sm;                                   // [KVM][nsplit][hd]: per head the source is one contiguous run
+    {
+        const uint32_t run4 = nsplit * hd / 4;           // float4 per head
+        constexpr int B = 4;
+        for (uint32_t e0 = threadIdx.x; e0 < KVM * run4; e0 += NT * B) {
+            float4 v[B];
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const uint32_t e = e0 + u * NT;
+                if (e < KVM * run4) {
+                    const uint32_t m = e / run4, j = e - m * run4;
+                    v[u] = __ldcg(reinterpret_cast<const float4 *>(a.ws_acc + (size_t)(g * KVM + m) * a.nsplit_max * hd) + j);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < B; u++) { const uint32_t e = e0 + u * NT; if (e < KVM * run4) reinterpret_cast<float4 *>(macc)[e] = v[u]; }
+        }
+    }
     if (warp < KVM) {
         const size_t base = (size_t)(g * KVM + warp) * a.nsplit_max;
-        float M = -FLT_MAX;
-        for (uint32_t s2 = lane; s2 < nsplit; s2 += 32) M = fmaxf(M, __ldcg(a.ws_m + base + s2));
-        M = warp_max(M);
+        float pm[2], pl[2];                              // nsplit_max <= 64: two slots per lane
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t s2 = lane + 32 * k;
+            pm[k] = (s2 < nsplit) ? __ldcg(a.ws_m + base + s2) : -FLT_MAX;
+            pl[k] = (s2 < nsplit) ? __ldcg(a.ws_l + base + s2) : 0.0f;
+        }
+        const float M = warp_max(fmaxf(pm[0], pm[1]));
         float L = 0.0f;
-        for (uint32_t s2 = lane; s2 < nsplit; s2 += 32) {
-            const float w = expf(__ldcg(a.ws_m + base + s2) - M);
-            wsc[warp * a.nsplit_max + s2] = w;
-            L += __ldcg(a.ws_l + base + s2) * w;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t s2 = lane + 32 * k;
+            if (s2 < nsplit) { const float w = expf(pm[k] - M); wsc[warp * a.nsplit_max + s2] = w; L += pl[k] * w; }
         }
         L = warp_sum(L);
         if (lane == 0) stat[2 * warp] = L;
     }
     __syncthreads();
+    AG_STAMP(g == 0, 17);
     uint32_t out_epoch = 0;
     if (TP) out_epoch = tp_epoch(a.tp, a.tp.signal_ph);
     for (uint32_t idx = threadIdx.x; idx < KVM * hd; idx += NT) {
         const uint32_t m = idx / hd, i = idx % hd;
-        const size_t base = (size_t)(g * KVM + m) * a.nsplit_max;
         float o = 0.0f;
 #pragma unroll 4
-        for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(__ldcg(a.ws_acc + (base + s2) * hd + i), wsc[m * a.nsplit_max + s2], o);
+        for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(macc[(m * nsplit + s2) * hd + i], wsc[m * a.nsplit_max + s2], o);
         const float ov = __fdiv_rn(o, stat[2 * m]);
         if (TP) tp_store(a.tp, a.tp.row_base + (g * KVM + m) * hd + i, ov, out_epoch); else a.xba[(size_t)(g * KVM + m) * hd + i] = ov;
     }
     if (threadIdx.x == 0) a.ticket[g] = 0;
+    AG_STAMP(g == 0, 18);
 }
 
 template <int KVM, bool TP = false>
@@ -1300,10 +1437,12 @@ __global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ uint32_t is_last;
     pdl_launch_dependents();
+    AG_STAMP(blockIdx.x == 0 && blockIdx.y == 0, 0);
     pdl_wait();
     const Dims &d = a.d;
     const uint32_t pos = __ldcg(&a.st->pos);
     const uint32_t range = __ldcg(&a.st->is_causal) ? pos + 1 : d.max_seq;
+    AG_STAMP(blockIdx.x == 0 && blockIdx.y == 0, 1);
     uint32_t chunk = (range + a.nsplit_max - 1) / a.nsplit_max;
     chunk = max(chunk, 32u);
     chunk = min((chunk + 7u) & ~7u, a.chunk_cap);

@@ -24,7 +24,7 @@ F_X, F_XBA, F_HB, F_Q, F_LOGITS, F_KROW, F_VROW, F_ACT_I8, F_ACT_SCALE = 0, 2, 4
 EXPORTS = [
     "nb200_last_error", "nb200_device_count", "nb200_engine_create", "nb200_engine_destroy", "nb200_get_config",
     "nb200_forward", "nb200_read_logits", "nb200_next_greedy", "nb200_decode_greedy", "nb200_read_buffer",
-    "nb200_write_x", "nb200_run_layer", "nb200_profile_tokens", "nb200_trace_token", "nb200_kernel_launches", "nb200_launches_per_token", "nb200_weight_bytes",
+    "nb200_write_x", "nb200_run_layer", "nb200_profile_tokens", "nb200_trace_token", "nb200_read_attn_trace", "nb200_kernel_launches", "nb200_launches_per_token", "nb200_weight_bytes",
     "nb200_op_rmsnorm", "nb200_op_q80_quantize", "nb200_op_q80_matvec", "nb200_op_f32_matvec",
     "nb200_op_q4k_quantize", "nb200_op_q4k_matvec",
     "nb200_op_q4k_quantize_blocks", "nb200_op_q4k_matvec_blocks",
@@ -71,6 +71,7 @@ def lib():
         L.nb200_run_layer.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.nb200_profile_tokens.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_uint32, f32p, u32p]
         L.nb200_trace_token.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint32, u32p]
+        L.nb200_read_attn_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.nb200_kernel_launches.restype = C.c_uint64
         L.nb200_kernel_launches.argtypes = [C.c_void_p]
         L.nb200_launches_per_token.restype = C.c_uint32
@@ -213,6 +214,12 @@ class Engine:
         buf = np.zeros(cap, np.uint64); n = C.c_uint32(0)
         _check(lib().nb200_trace_token(self.h, token, pos, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return buf[: n.value]
+
+    def attn_trace(self) -> np.ndarray:
+        """%globaltimer stamps (ns) of layer L/2's attention kernel in the last token (engine created with NB200_ATTN_DBG=1)."""
+        buf = np.zeros(32, np.uint64)
+        _check(lib().nb200_read_attn_trace(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return buf
 
     @property
     def launches(self) -> int:
