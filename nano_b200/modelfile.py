@@ -284,6 +284,24 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
     return {"path": path, "bytes": size, "spec": spec, "quant": quant, "gs": gs}
 
 
+def write_lora(spec: ModelSpec, rank: int = 8, alpha: int = 16, seed: int = 7, std: float = 0.05) -> bytes:
+    """A synthetic LoRA plug-in image in the reference's layout (infer.c:436-500): 256-byte header
+    {magic0, magic1, major, minor, model_type, config_length, rank, alpha, n_layer, n_embd, n_head, n_kv_head, n_hidden,
+    lora_config} then fp32 tensors wq_a (L,r,E), wq_b (L,E,r), wk_a (L,r,E), wk_b (L,kv,r), wv_a, wv_b, wo_a (L,r,E),
+    wo_b (L,E,r).  Both factors are non-zero so that every branch contributes."""
+    rng = np.random.default_rng(seed)
+    L, E, K = spec.n_layer, spec.n_embd, spec.kv_dim
+    hdr = np.zeros(64, dtype=np.uint32)
+    hdr[0], hdr[1], hdr[2], hdr[3] = 0x42443453, 0x41524F4C, 2025, 12
+    hdr[4], hdr[5] = spec.arch, 32
+    hdr[6:14] = [rank, alpha, L, E, spec.n_head, spec.n_kv_head, spec.n_hidden, 0]
+    parts = [hdr.tobytes()]
+    for rows_b in (E, K, K, E):
+        parts.append((rng.standard_normal(L * rank * E, dtype=np.float32) * np.float32(std)).tobytes())
+        parts.append((rng.standard_normal(L * rows_b * rank, dtype=np.float32) * np.float32(std)).tobytes())
+    return b"".join(parts)
+
+
 def cached_model(spec: ModelSpec, quant: int, gs: int = 128, seed: int = 39, cache_dir: Optional[str] = None,
                  cls_gain: float = 1.0, fast: bool = False) -> str:
     """Write (once) into a cache directory and return the path."""

@@ -171,6 +171,7 @@ class RefEngine:
             L.orh_open_buffer.restype = C.c_void_p
             L.orh_open_buffer.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint64]
             L.orh_close_file.argtypes = [C.c_void_p]
+            L.orh_load_lora.argtypes = [C.c_void_p, C.c_void_p]
             L.orh_forward.restype = f32p
             L.orh_forward.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
             L.orh_next.restype = C.c_uint32
@@ -223,6 +224,11 @@ class RefEngine:
         if self.h and self.from_file:
             self.L.orh_close_file(self.h)
         self.h = None
+
+    def load_lora(self, image: bytes) -> None:
+        """Attach a LoRA plug-in (the reference points into the buffer: keep it alive with the engine)."""
+        self._lora_image = np.frombuffer(bytes(image), dtype=np.uint8).copy()
+        self.L.orh_load_lora(self.h, self._lora_image.ctypes.data)
 
     def forward(self, token: int, pos: int, causal: int = 1) -> np.ndarray:
         p = self.L.orh_forward(self.h, int(token), int(pos), causal)

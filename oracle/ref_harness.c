@@ -90,6 +90,12 @@ Nano_Context *orh_open_buffer(uint8_t *buffer, uint32_t max_seq_len, float penal
  * (infer.c:372-378); tests simply leak buffer contexts. */
 void orh_close_file(Nano_Context *ctx) { llm_context_free(ctx); }
 
+/* LoRA plug-in (infer.c:408-545): the caller keeps `buffer` alive; ctx->lora makes llm_forward / generate_next_token take
+ * the low-rank branches (infer.c:792-808, 898-903). */
+void orh_load_lora(Nano_Context *ctx, uint8_t *buffer) {
+    ctx->lora = load_lora_from_buffer(ctx->llm, buffer);
+}
+
 float *orh_forward(Nano_Context *ctx, uint32_t token, uint32_t pos, uint32_t is_causal) {
     return llm_forward(ctx, token, pos, ctx->max_seq_len, is_causal, ctx->llm, ctx->lora);
 }

@@ -33,7 +33,7 @@ def full_report(rep, out_md, title):
         for row in r[2:]:
             f.write("| " + " | ".join(row[i][:70] for i in idx) + " |\n")
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     g = os.path.join(ROOT, "gpurun_out"); p = os.path.join(ROOT, "profiles")
     os.makedirs(p, exist_ok=True)
     for src, dst, title in [("r1/launches_multikernel.csv", "r1_launches_multikernel.md", "Round 1 - launch list, multi-kernel graph path, Nano-168M Q80 seq 512"),
@@ -45,3 +45,31 @@ if __name__ == "__main__":
     for b in os.listdir(os.path.join(g, "r1")) if os.path.isdir(os.path.join(g, "r1")) else []:
         if b.startswith("bench_") and b.endswith(".json"):
             open(os.path.join(p, "r1_" + b), "w").write(open(os.path.join(g, "r1", b)).read())
+
+
+def paths_table(out_md):
+    """profiles/r1_paths.md: one row per committed bench line (profiles/r1_bench_*.json)."""
+    p = os.path.join(ROOT, "profiles")
+    rows = []
+    for f in sorted(os.listdir(p)):
+        if not (f.startswith("r1_bench_") and f.endswith(".json")): continue
+        try: d = json.loads(open(os.path.join(p, f)).read().strip().splitlines()[-1])
+        except Exception: continue
+        if d.get("impl") == "reference": continue
+        cfg = d["config"]; tr = d.get("token_roofline") or {}
+        cb = d.get("cpu_baseline") or {}
+        gbs = tr.get("achieved_gbs_per_gpu", tr.get("achieved_gbs"))
+        rows.append((f, cfg["workload"].split(" greedy")[0], d["n_gpus"], ("tp" if cfg.get("parallelism", "").startswith("tp") else "replicas"), cfg.get("mode", ""), cfg["engine"].split(" (")[0],
+                     d["value"], d["e2e"]["value"], gbs, tr.get("frac_of_peak"), cb.get("value"), d.get("gpu_launches")))
+    with open(out_md, "w") as f:
+        f.write("# Round 1 - every measured path (B200, bench.py JSON lines committed beside this file)\n\n")
+        f.write("`value` = device-resident greedy decode tok/s (CUDA events, decode segment); `e2e` = per-token C-ABI calls with host buffers; "
+                "GB/s = algorithmic bytes per token x tok/s per GPU; frac = that / MEASURED_PEAKS.json hbm_gbs; CPU = the unmodified reference on the box's host cores (best thread count).\n\n")
+        f.write("| file | workload | GPUs | par. | mode | engine path | value tok/s | e2e tok/s | GB/s per GPU | frac of HBM peak | CPU reference tok/s | launches in timed region |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for r in rows:
+            fmt = lambda v, k=1: "" if v is None else (f"{v:.{k}f}" if isinstance(v, float) else str(v))
+            f.write(f"| `{r[0]}` | {r[1]} | {r[2]} | {r[3]} | {r[4]} | {r[5]} | {fmt(r[6])} | {fmt(r[7])} | {fmt(r[8])} | {fmt(r[9], 3)} | {fmt(r[10])} | {r[11]} |\n")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "paths":
+    paths_table(os.path.join(ROOT, "profiles", "r1_paths.md"))
