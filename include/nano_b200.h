@@ -104,6 +104,15 @@ int nb200_tp_export(nb200_engine *e, void *handle64);
 int nb200_tp_attach_ipc(nb200_engine *e, const void *handles /* tp_size x 64 bytes, rank order */);
 int nb200_tp_attach_local(nb200_engine *e, nb200_engine *const *group /* tp_size engines, rank order */);
 
+/* LoRA plug-in (fp32 low-rank branches on wq/wk/wv/wo of the Nano architecture):
+ *   nb200_lora_load    <- load_lora_from_buffer  infer/infer.c:513-519 (parse_lora_file :436-500); image_bytes 0 = trust the header
+ *   nb200_lora_enable  <- the use_lora switch of llm_forward / transformer_block_forward  infer/infer.c:713, 792, 898
+ *   nb200_lora_unload  <- free_lora              infer/infer.c:521-534
+ * While a plug-in is active the engine runs its multi-kernel path (two small extra kernels per site and layer). */
+int nb200_lora_load(nb200_engine *e, const uint8_t *image, uint64_t image_bytes);
+int nb200_lora_enable(nb200_engine *e, int on);
+int nb200_lora_unload(nb200_engine *e);
+
 int nb200_get_config(const nb200_engine *e, nb200_config *cfg);
 
 /* one token through the network; logits stay in HBM.  is_causal=0 is the reference's seq2seq mode

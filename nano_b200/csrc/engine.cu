@@ -112,6 +112,9 @@ struct nb200_engine {
     // tensor parallel (kernels.cuh "Tensor parallelism"): exchange block = [TpHdr | x | xba | hb]; d holds the LOCAL head counts
     uint32_t tp_rank = 0, tp_size = 1;
     bool tied = false;
+    // LoRA plug-in (nb200_lora_load): fp32 factors [L][rank][n] / [L][rows][rank] for q, k, v, o; scratch t [4][rank], o1 [E]
+    struct Lora { uint32_t rank = 0, alpha = 0; float *a[4] = {}, *b[4] = {}; float *t = nullptr, *o1 = nullptr; bool loaded = false, active = false; } lora;
+    bool path_cluster = false, path_mega = false;     // what the model would run on without a plug-in
     unsigned long long *attn_dbg = nullptr;          // NB200_ATTN_DBG=1: %globaltimer stamps of layer L/2's attention kernel
     uint32_t g_H = 0, g_KV = 0, g_q_dim = 0, g_kv_dim = 0;     // whole-model values (== d.* on one GPU)
     unsigned char *tp_block = nullptr; size_t tp_block_bytes = 0;
@@ -280,6 +283,19 @@ int run_layer(nb200_engine *e, uint32_t l) {
         e->prof_tag = 1;
         if ((r = run_matvec(e, EPI_QKV, e->qkv[l], a, true, e->num_sms))) return r;
     }
+    if (e->lora.active) {   // q/k/v LoRA branches on xb = rmsnorm(x)*gain, added before RoPE (infer.c:792-808)
+        const uint32_t rk = e->lora.rank;
+        LoraAArgs la{};
+        la.src = e->x; la.gain = e->norm_attn + (size_t)l * d.E; la.n = d.E; la.nmat = 3; la.rank = rk; la.t = e->lora.t; la.exact = d.exact;
+        for (int m = 0; m < 3; m++) la.A[m] = e->lora.a[m] + (size_t)l * rk * d.E;
+        if ((r = launch<LoraAArgs>(e, k_lora_a, dim3((3 * rk + kWarps - 1) / kWarps), dim3(kThreads), 3 * d.E * 4, la))) return r;
+        LoraBArgs lb{};
+        lb.t = e->lora.t; lb.nmat = 3; lb.rank = rk; lb.scale = (float)e->lora.alpha / (float)rk;
+        lb.rows[0] = d.q_dim; lb.rows[1] = d.kv_dim; lb.rows[2] = d.kv_dim;
+        lb.B[0] = e->lora.b[0] + (size_t)l * d.q_dim * rk; lb.B[1] = e->lora.b[1] + (size_t)l * d.kv_dim * rk; lb.B[2] = e->lora.b[2] + (size_t)l * d.kv_dim * rk;
+        lb.dst[0] = e->q; lb.dst[1] = e->kraw; lb.dst[2] = nullptr; lb.vcache = e->vc + l * kvl; lb.store = 0; lb.st = e->st; lb.d = d;
+        if ((r = launch<LoraBArgs>(e, k_lora_b, dim3((d.q_dim + 2 * d.kv_dim + 255) / 256), dim3(256), 0, lb))) return r;
+    }
     e->prof_tag = 2;
     if (!d.exact) {   // F2: head-norm + RoPE + split-KV attention
         AttnArgs a{};
@@ -313,9 +329,22 @@ int run_layer(nb200_engine *e, uint32_t l) {
         a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin; a.xba = e->xba; a.att = e->att_exact; a.st = e->st; a.d = d;
         if ((r = launch<AttnExactArgs>(e, k_attention_exact, dim3(d.H), dim3(kAttnThreads), 2 * d.hd * 4, a))) return r;
     }
+    if (e->lora.active) {   // o branch on the attention output; added to the O result before the residual (infer.c:898-903)
+        const uint32_t rk = e->lora.rank;
+        LoraAArgs la{};
+        la.src = e->xba; la.gain = nullptr; la.n = d.q_dim; la.nmat = 1; la.rank = rk; la.t = e->lora.t + 3 * rk; la.exact = d.exact;
+        la.A[0] = e->lora.a[3] + (size_t)l * rk * d.q_dim;
+        e->prof_tag = 3;
+        if ((r = launch<LoraAArgs>(e, k_lora_a, dim3((rk + kWarps - 1) / kWarps), dim3(kThreads), 3 * d.q_dim * 4, la))) return r;
+        LoraBArgs lb{};
+        lb.t = e->lora.t + 3 * rk; lb.nmat = 1; lb.rank = rk; lb.scale = (float)e->lora.alpha / (float)rk;
+        lb.rows[0] = d.E; lb.B[0] = e->lora.b[3] + (size_t)l * d.E * rk; lb.dst[0] = e->lora.o1; lb.store = 1; lb.st = e->st; lb.d = d;
+        if ((r = launch<LoraBArgs>(e, k_lora_b, dim3((d.E + 255) / 256), dim3(256), 0, lb))) return r;
+    }
     {   // F3: quantise(xba) + O matvec + residual
         MatvecArgs a = base_args(e);
         a.src = e->xba; a.gain = nullptr; a.out = e->x;
+        a.lora_add = e->lora.active ? e->lora.o1 : nullptr;
         a.tp = tp_args(e, 4 * l + 1, 4 * l + 2, e->tp_rank * e->wo[l].rows, e->tp_off_x);
         e->prof_tag = 3;
         if ((r = run_matvec(e, EPI_RESID, e->wo[l], a, false, e->num_sms))) return r;
@@ -953,6 +982,7 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
         if (T == 1 && !(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0) && (cl_default || cl_forced)) { if ((r = setup_cluster(e))) return r; }
         if (e->use_cluster) e->use_mega = false;
     }
+    e->path_cluster = e->use_cluster; e->path_mega = e->use_mega;
     if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
     guard.ok = true;
     *out = e;
@@ -971,7 +1001,7 @@ static int finish_paths(nb200_engine *e) {
         }
         if (r) return r;
     } else {
-        e->launches_per_token = 2 + 5 * e->d.L;
+        e->launches_per_token = 2 + (5 + (e->lora.active ? 4u : 0u)) * e->d.L;
     }
     return 0;
 }
@@ -984,6 +1014,65 @@ int nb200_engine_create(nb200_engine **out, const uint8_t *img, uint64_t image_b
 int nb200_engine_create_tp(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
                            uint32_t flags, uint32_t tp_rank, uint32_t tp_size) {
     return create_impl(out, img, image_bytes, max_seq_len, device, flags, tp_rank, tp_size);
+}
+
+// (de)activate the loaded plug-in: LoRA runs on the multi-kernel path only, so the path and the graph are rebuilt
+static int lora_set_active(nb200_engine *e, bool on) {
+    if (on == e->lora.active) return 0;
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    e->lora.active = on;
+    e->use_cluster = on ? false : e->path_cluster;
+    e->use_mega = on ? false : e->path_mega;
+    e->launches_per_token = (e->use_cluster || e->use_mega) ? 1u : 0u;
+    return finish_paths(e);
+}
+
+/* nb200_lora_load <- load_lora_from_buffer infer/infer.c:513-519 (parse_lora_file :436-500, malloc_fwd_buffer_with_lora :413-433).
+ * image_bytes == 0: trust the header like the reference does. */
+int nb200_lora_load(nb200_engine *e, const uint8_t *img, uint64_t image_bytes) {
+    if (!e || !img) return fail(NB200_EINVAL, "null argument");
+    if (e->tp_size > 1) return fail(NB200_EINVAL, "LoRA is not available on tensor-parallel engines");
+    if (e->lora.loaded) return fail(NB200_EINVAL, "a LoRA plug-in is already loaded");
+    const Dims &d = e->d;
+    if (d.arch != 0u) return fail(NB200_EINVAL, "LoRA plug-ins are defined for the Nano architecture only (infer.c:792)");
+    if (image_bytes && image_bytes < 256) return fail(NB200_EINVAL, "LoRA image truncated");
+    const uint32_t rank = rd_u32(img + 24), alpha = rd_u32(img + 28);
+    const uint32_t L = rd_u32(img + 32), E = rd_u32(img + 36), H = rd_u32(img + 40), KV = rd_u32(img + 44), F = rd_u32(img + 48);
+    if (L != d.L || E != d.E || H != d.H || KV != d.KV || F != d.F) return fail(NB200_EINVAL, "LoRA module does not fit the base model");
+    if (rank == 0 || rank > 64) return fail(NB200_EINVAL, "LoRA rank %u unsupported (1..64)", rank);
+    const uint64_t la = (uint64_t)L * rank * E;
+    const uint64_t lens[8] = {la, (uint64_t)L * d.q_dim * rank, la, (uint64_t)L * d.kv_dim * rank, la, (uint64_t)L * d.kv_dim * rank, la, (uint64_t)L * E * rank};
+    uint64_t total = 0; for (uint64_t v : lens) total += v;
+    if (image_bytes && image_bytes < 256 + total * 4) return fail(NB200_EINVAL, "LoRA image truncated (need %llu bytes)", (unsigned long long)(256 + total * 4));
+    CK(cudaSetDevice(e->device));
+    const float *p = reinterpret_cast<const float *>(img + 256);
+    for (int m = 0; m < 4; m++) {
+        DM(e->lora.a[m], lens[2 * m] * 4); DM(e->lora.b[m], lens[2 * m + 1] * 4);
+        CK(cudaMemcpy(e->lora.a[m], p, lens[2 * m] * 4, cudaMemcpyHostToDevice)); p += lens[2 * m];
+        CK(cudaMemcpy(e->lora.b[m], p, lens[2 * m + 1] * 4, cudaMemcpyHostToDevice)); p += lens[2 * m + 1];
+    }
+    DM(e->lora.t, 4 * rank * 4); DM(e->lora.o1, (size_t)E * 4);
+    e->lora.rank = rank; e->lora.alpha = alpha; e->lora.loaded = true;
+    return lora_set_active(e, true);
+}
+
+/* use_lora of llm_forward (infer.c:713, 792, 898): run with (1) or without (0) the loaded plug-in */
+int nb200_lora_enable(nb200_engine *e, int on) {
+    if (!e) return fail(NB200_EINVAL, "null engine");
+    if (!e->lora.loaded) return on ? fail(NB200_EINVAL, "no LoRA plug-in loaded") : 0;
+    return lora_set_active(e, on != 0);
+}
+
+/* nb200_lora_unload <- free_lora infer/infer.c:521-534 */
+int nb200_lora_unload(nb200_engine *e) {
+    if (!e) return fail(NB200_EINVAL, "null engine");
+    if (!e->lora.loaded) return 0;
+    int r = lora_set_active(e, false);
+    for (int m = 0; m < 4; m++) { e->lora.a[m] = nullptr; e->lora.b[m] = nullptr; }      // device memory is released with the engine
+    e->lora.loaded = false; e->lora.rank = 0;
+    return r;
 }
 
 int nb200_tp_export(nb200_engine *e, void *handle64) {

@@ -144,13 +144,41 @@ void free_llm(LLM *llm, Tokenizer *tk) {
     free(llm);
 }
 
-LoRA *load_lora_from_buffer(LLM *llm, uint8_t *buffer) {
-    (void)llm; (void)buffer;
-    fprintf(stderr, "nano_b200: LoRA adapters are not supported by the B200 engine (SURVEY 8f row f4)\n");
-    exit(EXIT_FAILURE);
+/* infer.c:436-519: the factors are uploaded to HBM; the LoRA struct keeps the reference's host view (config + pointers into
+ * the caller's buffer) for hosts that inspect it. */
+static LoRA *lora_from_image(LLM *llm, uint8_t *buffer, uint64_t bytes) {
+    if (!buffer) die("load_lora: null buffer");
+    if (nb200_lora_load(engine_of(llm), buffer, bytes) != NB200_OK) die("load_lora");
+    LoRA *p = (LoRA *)platform_calloc(1, sizeof(LoRA));
+    p->data = (float *)(void *)buffer;
+    memcpy(&p->config, buffer + 24, sizeof(LoRA_Config));        /* rank, alpha, n_layer, n_embd, n_head, n_kv_head, n_hidden, lora_config */
+    const uint64_t L = llm->config.n_layer, E = llm->config.n_embd, r = p->config.lora_rank;
+    const uint64_t kv = (E / llm->config.n_head) * llm->config.n_kv_head;
+    float *f = (float *)(void *)(buffer + 256);
+    p->params.wq_lora_a = f; f += L * r * E;  p->params.wq_lora_b = f; f += L * E * r;
+    p->params.wk_lora_a = f; f += L * r * E;  p->params.wk_lora_b = f; f += L * kv * r;
+    p->params.wv_lora_a = f; f += L * r * E;  p->params.wv_lora_b = f; f += L * kv * r;
+    p->params.wo_lora_a = f; f += L * r * E;  p->params.wo_lora_b = f;
+    return p;
 }
-LoRA *load_lora(LLM *llm, char *lora_path) { (void)lora_path; return load_lora_from_buffer(llm, NULL); }
-void free_lora(LLM *llm, LoRA *lora) { (void)llm; (void)lora; }
+LoRA *load_lora_from_buffer(LLM *llm, uint8_t *buffer) { return lora_from_image(llm, buffer, 0); }
+LoRA *load_lora(LLM *llm, char *lora_path) {
+    FILE *fp = fopen(lora_path, "rb");
+    if (!fp) { fprintf(stderr, "Couldn't open LoRA module file %s\n", lora_path); exit(EXIT_FAILURE); }
+    fseek(fp, 0, SEEK_END);
+    const uint64_t n = (uint64_t)ftell(fp);
+    rewind(fp);
+    uint8_t *buf = (uint8_t *)platform_calloc(n + 1, 1);
+    if (!buf) die("load_lora: allocation failed");
+    if (fread(buf, 1, n, fp) != n) { fclose(fp); exit(EXIT_FAILURE); }
+    fclose(fp);
+    return lora_from_image(llm, buf, n);
+}
+/* infer.c:521-534 frees interior pointers of a single allocation (undefined behaviour); here: drop the device copy and the struct */
+void free_lora(LLM *llm, LoRA *lora) {
+    if (llm) nb200_lora_unload(engine_of(llm));
+    free(lora);
+}
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* context / sampler (infer.c:548-581, 1111-1127)                                                          */
@@ -202,9 +230,10 @@ void llm_context_free(Nano_Context *ctx) {
 /* one token (infer.c:971-1018, 1135-1193)                                                                 */
 /* ------------------------------------------------------------------------------------------------------ */
 float *llm_forward(Nano_Context *ctx, uint32_t token, uint32_t pos, uint32_t max_seq_len, uint32_t is_causal, LLM *llm, LoRA *lora) {
-    (void)max_seq_len; (void)lora;
+    (void)max_seq_len;
     notify_forward(ctx);
     nb200_engine *e = engine_of(llm);
+    if (nb200_lora_enable(e, lora != NULL) != NB200_OK) die("llm_forward (use_lora)");
     if (nb200_forward(e, token, pos, is_causal) != NB200_OK) die("llm_forward");
     if (nb200_read_logits(e, llm->state.logits) != NB200_OK) die("llm_forward (logits)");
     return llm->state.logits;
@@ -257,6 +286,7 @@ uint32_t generate_next_token(Nano_Context *ctx, uint32_t *output_ids, uint32_t p
         notify_forward(ctx);
         if (is_prefilling != 1) notify(ctx, -1, NANO_PH_SAMPLE);
         uint32_t next = 0;
+        if (nb200_lora_enable(e, ctx->lora != NULL) != NB200_OK) die("generate_next_token (use_lora)");
         if (nb200_next_greedy(e, output_ids, pos, is_prefilling == 1, sp->repetition_penalty, &next) != NB200_OK) die("generate_next_token");
         return next;
     }

@@ -136,6 +136,7 @@ struct MatvecArgs {
     unsigned long long *dbg;     // optional: CTA 0 / thread 0 clock64() stamps inside the phase (tools/gpu_trace.py)
     Dims d;
     TpArgs tp;                   // tensor-parallel exchange (k_matvec<..., TP=true> only)
+    const float *lora_add;       // RESID only: LoRA branch of the O projection, added to the matvec result BEFORE the residual (infer.c:898-908)
 };
 #define NB_STAMP(ptr, k) do { if ((ptr) && blockIdx.x == 0 && threadIdx.x == 0) (ptr)[k] = clock64(); } while (0)
 
@@ -845,6 +846,7 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 else if (EPI == EPI_RESID) {
                     if (lane == 0) {
                         const float xo = kFirst ? xres[r] : (TP ? __uint_as_float((uint32_t)__ldcg(out_ll + rbase + row)) : __ldcg(a.out + rbase + row));
+                        if (a.lora_add) v = __fadd_rn(v, __ldcg(a.lora_add + rbase + row));       // accum(xb2, o1) precedes x += xb2
                         const float xn = __fadd_rn(xo, v);
                         if (TP) tp_store(a.tp, rbase + row, xn, out_epoch); else a.out[row] = xn;
                     }
@@ -994,7 +996,7 @@ __global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
             const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_ref(-res[0])));
             a.out[row] = __fmul_rn(__fmul_rn(res[0], sg), res[1]);
         } else if (EPI == EPI_STORE) a.out[row] = res[0];
-        else if (EPI == EPI_RESID) a.out[row] = __fadd_rn(a.out[row], res[0]);
+        else if (EPI == EPI_RESID) a.out[row] = __fadd_rn(a.out[row], a.lora_add ? __fadd_rn(res[0], a.lora_add[row]) : res[0]);
         else if (EPI == EPI_QKV) {
             if (row < d.q_dim) a.out[row] = res[0];
             else if (row < d.q_dim + d.kv_dim) a.out_k[row - d.q_dim] = res[0];
@@ -1004,6 +1006,70 @@ __global__ void __launch_bounds__(256) k_matvec_f32_exact(const MatvecArgs a) {
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LoRA branches (infer.c:792-808 q/k/v on the normalised fp32 activation, :898-903 o on the attention output):
+//   t = A x          (rank dots of length n; fp32 `matmul`, infer.c:637-651)
+//   y = (alpha/rank) (B t), then accum(base, y)      (`scale` :595, `accum` :589)
+// Two small kernels per site; they run only when a plug-in is loaded (nb200_lora_load), on the multi-kernel path.
+// ------------------------------------------------------------------------------------------------
+struct LoraAArgs {
+    const float *src; const float *gain;    // gain != nullptr: rmsnorm(src) * gain first (the q/k/v site reads xb)
+    const float *A[3];                      // [rank][n] of this layer, one per branch
+    uint32_t n, nmat, rank;
+    float *t;                               // out [nmat][rank]
+    uint32_t exact;
+};
+__global__ void __launch_bounds__(kThreads) k_lora_a(const LoraAArgs a) {
+    extern __shared__ __align__(16) unsigned char act[];
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    float *x = reinterpret_cast<float *>(act);
+    prep_f32<kThreads>(a.src, a.gain, (int)a.n, a.exact != 0, x, x + a.n, red);       // smem: 3n floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t u = blockIdx.x * kWarps + warp;
+    if (u >= a.nmat * a.rank) return;
+    const uint32_t m = u / a.rank, j = u - m * a.rank;
+    const float *row = a.A[m] + (size_t)j * a.n;
+    float val = 0.0f;
+    if (a.exact) {
+        if (lane == 0) for (uint32_t i = 0; i < a.n; i++) val = __fadd_rn(val, __fmul_rn(__ldg(row + i), x[i]));
+    } else {
+        for (uint32_t i = lane; i < a.n; i += 32) val = fmaf(__ldg(row + i), x[i], val);
+        val = warp_sum(val);
+    }
+    if (lane == 0) a.t[u] = val;
+}
+
+struct LoraBArgs {
+    const float *t;                         // [nmat][rank]
+    const float *B[3]; uint32_t rows[3];    // [rows][rank] of this layer
+    uint32_t nmat, rank;
+    float scale;                            // (float)alpha / (float)rank
+    float *dst[3];                          // accumulate targets (q, raw k, nullptr => V-cache row of `pos`) or the o1 buffer
+    float *vcache;                          // V cache base of this layer [KV][max_seq][hd]
+    uint32_t store;                         // 1: dst[0][i] = y (o site);  0: dst += y
+    const DevState *st; Dims d;
+};
+__global__ void __launch_bounds__(256) k_lora_b(const LoraBArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    uint32_t i = blockIdx.x * 256 + threadIdx.x, m = 0;
+    while (m < a.nmat && i >= a.rows[m]) { i -= a.rows[m]; m++; }
+    if (m >= a.nmat) return;
+    const float *row = a.B[m] + (size_t)i * a.rank, *t = a.t + m * a.rank;
+    float val = 0.0f;
+    for (uint32_t j = 0; j < a.rank; j++) val = __fadd_rn(val, __fmul_rn(__ldg(row + j), __ldcg(t + j)));      // matmul order, any mode
+    val = __fmul_rn(val, a.scale);
+    float *dst = a.dst[m];
+    if (!dst) {
+        const uint32_t pos = __ldcg(&a.st->pos), h = i / a.d.hd, e = i % a.d.hd;
+        dst = a.vcache + ((size_t)h * a.d.max_seq + pos) * a.d.hd + e;
+        i = 0;
+    }
+    dst[i] = a.store ? val : __fadd_rn(dst[i], val);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ EXPORTS = [
     "nb200_op_rmsnorm", "nb200_op_q80_quantize", "nb200_op_q80_matvec", "nb200_op_f32_matvec",
     "nb200_op_q4k_quantize", "nb200_op_q4k_matvec",
     "nb200_op_q4k_quantize_blocks", "nb200_op_q4k_matvec_blocks",
+    "nb200_lora_load", "nb200_lora_enable", "nb200_lora_unload",
     "nb200_engine_create_tp", "nb200_tp_export", "nb200_tp_attach_ipc", "nb200_tp_attach_local",
 ]
 
@@ -86,6 +87,9 @@ def lib():
         L.nb200_op_q4k_matvec.argtypes = [f32p, f32p, u8p, C.c_uint32, C.c_uint32]
         L.nb200_op_q4k_quantize_blocks.argtypes = [u8p, f32p, C.c_uint64]
         L.nb200_op_q4k_matvec_blocks.argtypes = [f32p, u8p, u8p, C.c_uint32, C.c_uint32]
+        L.nb200_lora_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.nb200_lora_enable.argtypes = [C.c_void_p, C.c_int]
+        L.nb200_lora_unload.argtypes = [C.c_void_p]
         L.nb200_host_expf_ref.restype = C.c_float
         L.nb200_host_expf_ref.argtypes = [C.c_float]
         L.nb200_host_expf_ref_array.argtypes = [f32p, f32p, C.c_uint64]
@@ -135,6 +139,20 @@ class Engine:
         self.path = {3: "cluster-resident kernel (16-CTA cluster, DSMEM activations, TMA weight ring)",
                      2: "persistent megakernel (cooperative launch, L2 grid barriers)",
                      1: "multi-kernel CUDA graph with PDL", 0: "multi-kernel direct launches"}[int(cfg.reserved[0])]
+
+    # ---- LoRA plug-in ----
+    def lora_load(self, image: bytes) -> None:
+        buf = np.frombuffer(bytes(image), dtype=np.uint8)
+        _check(lib().nb200_lora_load(self.h, buf.ctypes.data, buf.size))
+        self._refresh()
+
+    def lora_enable(self, on: bool) -> None:
+        _check(lib().nb200_lora_enable(self.h, 1 if on else 0))
+        self._refresh()
+
+    def lora_unload(self) -> None:
+        _check(lib().nb200_lora_unload(self.h))
+        self._refresh()
 
     # ---- tensor parallel ----
     def tp_export(self) -> bytes:

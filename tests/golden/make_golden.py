@@ -7,6 +7,7 @@ Run in the build container (needs /root/reference):   python tests/golden/make_g
   sort6_kat.json       seq2seq answers of the reference on it (README.md:379 "114515 -> 111455" and four more)
   toy_logits.npz       teacher-forced logits of the strict reference on seeded synthetic toy files
                        (nano_b200/modelfile.py presets, seed 39) at a few positions, F32 / Q80 / Q4K
+  lora_logits.npz      the same with a seeded synthetic LoRA plug-in (rank 8, alpha 16) attached to toy-nano
   q4k_kat.npz          Q4K op-level vectors following the recipe of infer/tools/export_q4k.c:394-450
                        (seed 39 xorshift, d=8, n=768): reference quantize_tensor_q4k bytes + matmul_q4k outputs
 """
@@ -65,6 +66,19 @@ def main():
         r.close()
         print(key, out[key].shape, float(np.abs(out[key]).max()))
     np.savez_compressed(os.path.join(HERE, "toy_logits.npz"), **out)
+
+    # LoRA plug-in (infer.c:792-808, 898-903): strict-reference logits with a seeded synthetic plug-in attached
+    lora_out = {}
+    for quant, gs in [(mf.QUANT_F32, 128), (mf.QUANT_Q80, 64)]:
+        spec = mf.PRESETS["toy-nano"]
+        path = mf.cached_model(spec, quant, gs)
+        r = ob.RefEngine(path, TOY_SEQ, "strict")
+        r.load_lora(mf.write_lora(spec, 8, 16, seed=7))
+        toks = mf.teacher_tokens(TOY_SEQ, spec.vocab)
+        rows = [r.forward(toks[pos], pos) for pos in range(TOY_SEQ)]
+        lora_out[f"toy-nano_{quant:02x}_{gs}"] = np.stack([rows[p] for p in TOY_POSITIONS])
+        r.close()
+    np.savez_compressed(os.path.join(HERE, "lora_logits.npz"), **lora_out)
 
     # Noise floor of the reference itself: max |logit(fast build) - logit(strict build)| of the SAME source on the
     # SAME file (SURVEY finding 11).  The fast-mode GPU tolerance is max(north-star tolerance, 1.5 x this floor).
