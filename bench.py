@@ -233,7 +233,7 @@ def run_reference_arm(args, spec, quant, gs, seq, path):
     line = {"impl": "reference", "metric": "decode tokens/sec at batch=1", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": (time.time() - t0) * 1e3 / max(1, args.steps + args.warmup),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint8->int32 + f32" if quant == mf.QUANT_Q80 else "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "seq": seq, "prompt": PROMPT},
+            "data": "synthetic", "config": {"workload": f"{args.workload} greedy decode, seq={seq}, prompt={PROMPT}, max_seq_len={seq}", "mode": "reference CPU engine (oracle/_ref, Makefile flags; oracle port if absent)"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

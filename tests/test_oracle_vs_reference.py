@@ -163,3 +163,26 @@ def test_expf_ref_equals_host_libm():
         want = np.empty_like(x)
         L.nor_expf_array(want.ctypes.data_as(ob.f32p), x.ctypes.data_as(ob.f32p), x.size)
         assert_bits_equal(E.host_expf_ref(x), want, "expf")
+
+
+@needs_ref
+def test_lora_golden_is_what_the_reference_computes():
+    """Pins tests/golden/lora_logits.npz (the GPU LoRA tests' fixture) to the unmodified strict reference with the same
+    synthetic plug-in, and checks that the plug-in writer's layout is the one parse_lora_file reads (infer.c:436-500)."""
+    spec = mf.PRESETS["toy-nano"]
+    lora = mf.write_lora(spec, 8, 16, seed=7)
+    assert len(lora) == 256 + 4 * spec.n_layer * 8 * (4 * spec.n_embd + 2 * spec.n_embd + 2 * spec.kv_dim)
+    gold = np.load(os.path.join(GOLDEN, "lora_logits.npz"))
+    for quant, gs in [(mf.QUANT_F32, 128), (mf.QUANT_Q80, 64)]:
+        path = mf.cached_model(spec, quant, gs)
+        plain = ob.RefEngine(path, 24, "strict")
+        r = ob.RefEngine(path, 24, "strict"); r.load_lora(lora)
+        toks = mf.teacher_tokens(24, spec.vocab)
+        rows = []
+        for pos in range(24):
+            lg = r.forward(toks[pos], pos); base = plain.forward(toks[pos], pos)
+            if pos in (0, 1, 7, 23):
+                rows.append(lg)
+                assert np.abs(lg - base).max() > 1e-2, "the plug-in must change the logits"
+        assert_bits_equal(np.stack(rows), gold[f"toy-nano_{quant:02x}_{gs}"], f"lora golden {quant:#x}")
+        r.close(); plain.close()
