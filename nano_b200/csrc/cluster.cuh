@@ -22,7 +22,6 @@ namespace nb {
 
 constexpr int kCluster = 16;
 constexpr int kMaxStages = 16;
-constexpr uint32_t kEmptyArrivals = 4;      // arrivals that free a ring stage: one per 8-row slice of a 32-row tile (fewer slices arrive with a multiple)
 
 struct ClPhase {              // one matvec phase of the per-token schedule (identical for all ranks)
     uint64_t stream_off;      // byte offset of this phase's first weight tile inside a rank's stream
@@ -62,9 +61,6 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -186,47 +182,6 @@ __device__ __forceinline__ float cl_row_dot(const unsigned char *wrow, const flo
     return val;
 }
 
-// Four lanes = one weight row resident in shared memory (lane = 4*r + sub, 8 rows per warp pass).  Lane `sub` owns 1/4 of
-// every quantisation group (gs = 128: 32 bytes, gs = 64: 16 bytes), so the 8 lanes of a quarter-warp hit 8 different
-// 16-byte bank groups (row stride = n + 16).  The group's integer dot is completed with two xor-shuffles (exact), then
-// every lane forms the same fp32 term and adds it in the reference's left-to-right group order (infer.c:668-674).
-template <int LPG>
-__device__ __forceinline__ float cl_row_dot4(const unsigned char *wrow, const float *srow, uint32_t n, const unsigned char *act, int sub, bool on) {
-    constexpr uint32_t gs = LPG * 16, per = gs / 4;          // bytes of a group per lane
-    static_assert(per == 16 || per == 32, "4 lanes per row need gs 64 or 128");
-    const unsigned char *codes = act;
-    const float *xs = reinterpret_cast<const float *>(act + ((n + 15) & ~15));
-    const uint32_t G = n / gs;
-    float val = 0.0f;
-    for (uint32_t gi = 0; gi < G; gi++) {
-        int i0 = 0;
-        if (on) {
-#pragma unroll
-            for (uint32_t b = 0; b < per; b += 16) {
-                const int4 w = *reinterpret_cast<const int4 *>(wrow + gi * gs + sub * per + b), x = *reinterpret_cast<const int4 *>(codes + gi * gs + sub * per + b);
-                i0 = __dp4a(w.x, x.x, i0); i0 = __dp4a(w.y, x.y, i0); i0 = __dp4a(w.z, x.z, i0); i0 = __dp4a(w.w, x.w, i0);
-            }
-        }
-        i0 += __shfl_xor_sync(0xffffffffu, i0, 1);
-        i0 += __shfl_xor_sync(0xffffffffu, i0, 2);
-        if (on) val = __fadd_rn(val, __fmul_rn(__fmul_rn((float)i0, srow[gi]), xs[gi]));
-    }
-    return val;
-}
-
-// the 4 lanes of a row share the 16 replicas: lane `sub` writes ranks 4*sub .. 4*sub+3
-__device__ __forceinline__ void scatter_row4_f32(float *local_slot, float v, int sub, bool active) {
-    const uint32_t a = smem_u32(local_slot);
-#pragma unroll
-    for (int k = 0; k < kCluster / 4; k++) {
-        if (active) {
-            uint32_t remote;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(a), "r"(sub * (kCluster / 4) + k));
-            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
-        }
-    }
-}
-
 // every lane writes its own value into the same slot of all 16 replicas
 __device__ __forceinline__ void scatter_lane_f32(float *local_slot, float v, bool active) {
     const uint32_t a = smem_u32(local_slot);
@@ -323,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
     float *attn_ws = reinterpret_cast<float *>(sm + g.off_attn);
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kEmptyArrivals); stage_tile[s] = 0xffffffffu; }
+        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); stage_tile[s] = 0xffffffffu; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -370,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
                 gain = reinterpret_cast<const float *>(ring.buf + (size_t)hs * ring.stage_bytes);
             }
             cl_prep_q80<kThreads>(src, gain, (int)c.n, (int)gs, act, ms.red);        // ends with __syncthreads()
-            if (c.has_gain && threadIdx.x == 32) mbar_arrive_n(&ring.empty[hs], kEmptyArrivals);
+            if (c.has_gain && threadIdx.x == 32) mbar_arrive(&ring.empty[hs]);
             CL_STAMP();
             // ---- weight tiles: warp 0 streams, warps 1..15 each own whole tiles (one lane per row) ----
             if (warp == 0) {
@@ -380,39 +335,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArg
                 }
                 __syncwarp();
             } else {
-                // work unit = (tile j, slice q): 8 rows x 4 lanes; a tile of T rows has Q = T/8 slices, so even a phase with two
-                // or three tiles keeps most warps busy.  Every slice arrives on the stage's empty barrier (kEmptyArrivals total).
-                const uint32_t R = min(8u, c.rows_per_tile), Q = c.rows_per_tile / R;
-                const int r8 = lane >> 2, sub = lane & 3;
-                for (uint32_t uu = (uint32_t)warp - 1; uu < c.ntiles * Q; uu += kWarps - 1) {
-                    const uint32_t j = uu / Q, qd = uu - j * Q;
+                for (uint32_t j = (uint32_t)warp - 1; j < c.ntiles; j += kWarps - 1) {
                     const uint32_t s = ring_wait_tile(ring, t0w + j);
                     const uint32_t rows = min(c.rows_per_tile, c.rows_per_rank - j * c.rows_per_tile);
                     const unsigned char *tile = ring.buf + (size_t)s * ring.stage_bytes;
                     const float *tscales = reinterpret_cast<const float *>(tile + (size_t)rows * c.row_stride);
-                    const uint32_t rt = qd * R + (uint32_t)r8;                       // row within the tile
-                    const bool on = (uint32_t)r8 < R && rt < rows;
-                    float v = cl_row_dot4<LPG>(tile + (size_t)(on ? rt : 0) * c.row_stride, tscales + (size_t)(on ? rt : 0) * c.gs_stride, c.n, act, sub, on);
+                    const bool on = (uint32_t)lane < rows;
+                    float v = 0.0f;
+                    if (on) v = cl_row_dot<LPG>(tile + (size_t)lane * c.row_stride, tscales + (size_t)lane * c.gs_stride, c.n, act);
                     // release the stage before the epilogue (the arrive has release semantics; DSMEM stores issued before it
                     // would have to be acknowledged by 16 SMs first)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_n(&ring.empty[s], kEmptyArrivals / Q);
-                    const uint32_t row = rank * c.rows_per_rank + j * c.rows_per_tile + rt;   // row of the fused matrix
-                    if (c.epi == EPI_SWIGLU) {            // rows (2i, 2i+1) = (w1 row i, w3 row i) sit 4 lanes apart; infer.c:937-944
-                        const float v3 = __shfl_down_sync(0xffffffffu, v, 4);
+                    if (lane == 0) mbar_arrive(&ring.empty[s]);
+                    const uint32_t row = rank * c.rows_per_rank + j * c.rows_per_tile + (uint32_t)lane;   // row of the fused matrix
+                    if (c.epi == EPI_SWIGLU) {            // lanes (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
+                        const float v3 = __shfl_down_sync(0xffffffffu, v, 1);
                         const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
-                        scatter_row4_f32(hb_s + (row >> 1), __fmul_rn(__fmul_rn(v, sg), v3), sub, on && !(rt & 1));
+                        scatter_lane_f32(hb_s + (row >> 1), __fmul_rn(__fmul_rn(v, sg), v3), on && !(lane & 1));
                     } else if (c.epi == EPI_RESID) {
-                        scatter_row4_f32(x_s + row, on ? __fadd_rn(x_s[row], v) : 0.0f, sub, on);
+                        scatter_lane_f32(x_s + row, on ? __fadd_rn(x_s[row], v) : 0.0f, on);
                     } else if (c.epi == EPI_QKV) {
                         float *dst = q_s + row;
                         if (row >= d.q_dim + d.kv_dim) {
                             const uint32_t cc = row - d.q_dim - d.kv_dim, h = cc / d.hd, e = cc % d.hd;
                             dst = vrow_s + cc;
-                            if (on && sub == 0) g.vc[(size_t)c.layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + e] = v;
+                            if (on) g.vc[(size_t)c.layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + e] = v;
                         } else if (row >= d.q_dim) dst = kraw_s + (row - d.q_dim);
-                        scatter_row4_f32(dst, v, sub, on);
-                    } else if (on && sub == 0) {       // EPI_CLS: infer.c:1156-1167 penalty, then first-max argmax :1026-1037 (rows ascend per lane)
+                        scatter_lane_f32(dst, v, on);
+                    } else if (on) {       // EPI_CLS: infer.c:1156-1167 penalty, then first-max argmax :1026-1037 (rows ascend per lane)
                         if (pen != 1.0f && __ldcg(g.seen + row)) v = __fdiv_rn(v, pen);
                         g.logits[row] = v;
                         if (v > bestv) { bestv = v; besti = row; }
