@@ -236,24 +236,6 @@ __device__ __forceinline__ void cl_prep_q80(const float *src, const float *gain,
     __syncthreads();
 }
 
-// tile rows from shared memory into the register tile used by q80_consume
-template <int LPG>
-__device__ __forceinline__ void q80_load_smem(Q80Tile<2> &t, const unsigned char *codes, const float *scales, uint32_t n, uint32_t k0) {
-    constexpr uint32_t gs = LPG * 16;
-    const int lane = threadIdx.x & 31;
-    const uint32_t G = n / gs;
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const uint32_t k = k0 + s * 512 + lane * 16;
-        const bool on = k < n;
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            t.w[s][r] = on ? *reinterpret_cast<const int4 *>(codes + (size_t)r * n + k) : make_int4(0, 0, 0, 0);
-            t.ws[s][r] = on ? scales[r * G + k / gs] : 0.0f;
-        }
-    }
-}
-
 // ---------------------------------------------------------------- the kernel
 template <int LPG, int KVM>
 __global__ void __launch_bounds__(kThreads, 1) k_decode_cluster(const ClusterArgs g) {
