@@ -14,7 +14,8 @@
  *   - ctx->observation may be NULL (the reference dereferences it unconditionally: infer.c:756 ff.);
  *   - with a hook installed, the per-phase notifications of one token fire in the reference's order BEFORE the
  *     token's single device launch (the GUI only draws a layer diagram from them, ui_llm.c:695-705);
- *   - LoRA adapters are rejected (not on any BASELINE configuration).
+ *   - LoRA plug-ins are uploaded to the GPU at load time (the reference keeps pointers into the caller's buffer);
+ *     free_lora releases the device copy and the struct instead of free()ing interior pointers (infer.c:521-534).
  */
 #define _GNU_SOURCE
 #include <fcntl.h>

@@ -73,3 +73,23 @@ def paths_table(out_md):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "paths":
     paths_table(os.path.join(ROOT, "profiles", "r1_paths.md"))
+
+
+def round_outputs(src_dir, tag="r1"):
+    """Evidence of tools/round_gpu_run.sh (gpurun_out/<dir>) -> tracked summaries under profiles/."""
+    p = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(src_dir)):
+        path = os.path.join(src_dir, f)
+        if f.startswith("bench_") and f.endswith(".json") and os.path.getsize(path) > 10:
+            open(os.path.join(p, f"{tag}_{f}"), "w").write(open(path).read())
+        elif f.startswith("launches_") and f.endswith(".csv"):
+            launch_list(path, os.path.join(p, f"{tag}_{f[:-4]}.md"), f"Round 1 - launch list ({f[9:-4]}): every kernel launched by the bench command under ncu")
+        elif f.endswith(".ncu-rep"):
+            full_report(path, os.path.join(p, f"{tag}_ncu_full_{f[5:-8]}.md"), f"Round 1 - ncu --set full ({f[5:-8]})")
+        elif f in ("pytest_gpu.log", "smoke.log"):
+            open(os.path.join(p, f"{tag}_{f}"), "w").write(open(path).read())
+    paths_table(os.path.join(p, f"{tag}_paths.md"))
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "round":
+    round_outputs(sys.argv[2])
