@@ -222,9 +222,9 @@ int run_matvec(nb200_engine *e, int epi, const Mat &m, MatvecArgs a, bool norm, 
         }
     }
     const uint32_t total_warps = (uint32_t)num_sms * grid_mult() * kWarps;
-    // Row blocks are dealt round-robin to the warps, so the last wave is partly empty: 4 rows per block only where there
-    // are enough waves to amortise that tail (classifiers); 2 rows (with 2 tiles in flight) otherwise.
-    int rb = (m.rows >= total_warps * (d.quant == 0x80u ? 32 : 8)) ? 4 : 2;
+    // 4 rows per block once there are >= 2 waves of such blocks, else 2.  (Measured on Qwen3-4B W1|W3, 19456 rows: RB=4 372
+    // tok/s vs RB=2 359, although RB=4 leaves the third wave almost empty.)
+    int rb = (m.rows >= total_warps * 8) ? 4 : 2;
     // few long rows (O / W2 of the larger models): one row per warp keeps every warp busy, 4 tiles in flight each
     if (d.quant == 0x80u && epi != EPI_SWIGLU && m.rows <= total_warps && m.n >= 2048 && !getenv("NB200_NO_RB1")) rb = 1;
     const int lpg = (d.quant == 0x80u) ? (int)(d.gs / 16) : 8;
