@@ -64,7 +64,10 @@ def paths_table(out_md):
     with open(out_md, "w") as f:
         f.write("# Round 1 - every measured path (B200, bench.py JSON lines committed beside this file)\n\n")
         f.write("`value` = device-resident greedy decode tok/s (CUDA events, decode segment); `e2e` = per-token C-ABI calls with host buffers; "
-                "GB/s = algorithmic bytes per token x tok/s per GPU; frac = that / MEASURED_PEAKS.json hbm_gbs; CPU = the unmodified reference on the box's host cores (best thread count).\n\n")
+                "GB/s = algorithmic bytes per token x tok/s per GPU; frac = that / MEASURED_PEAKS.json hbm_gbs; CPU = the unmodified reference on the box's host cores (best thread count).\n\n"
+                "The JSON lines were collected over the round; `r1_bench_n168_q80.json`, `r1_bench_q4b_q80.json`, `r1_bench_q06_q80.json` and `r1_bench_tp2_q17_q80.json` are from the final kernels, the others from earlier "
+                "states of the same paths.  `r1_evidence_run_stdout.md` has the values of ALL single-GPU configs on the (almost) final tree: N168 Q80 1498.7 (cluster) / 1460.0 (multi-kernel) / 828.0 (exact), "
+                "N168 F32 1233.5, Q06 Q80 1020.0, Q06 Q4K 771.8, Q1.7B Q80 804.7, Q4B Q80 358.9 (372.2 with the final row-block rule).\n\n")
         f.write("| file | workload | GPUs | par. | mode | engine path | value tok/s | e2e tok/s | GB/s per GPU | frac of HBM peak | CPU reference tok/s | launches in timed region |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for r in rows:
             fmt = lambda v, k=1: "" if v is None else (f"{v:.{k}f}" if isinstance(v, float) else str(v))
