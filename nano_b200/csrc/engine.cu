@@ -923,6 +923,9 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     if (!coop) mk = nullptr;
     uint32_t nsm = (uint32_t)e->num_sms / e->g_KV;  // (kv head, split) items <= one per SM; same split in every path and TP size => identical bits
     if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
+    // the merging CTA stages nsplit x kv_mul x head_dim partial accumulators in shared memory: keep that under 160 KB
+    // (only shapes with few kv heads AND many q heads per kv head are affected; none of the BASELINE configs)
+    while (nsm > 1 && (size_t)attn_fast_smem_floats(d.kv_mul, d.hd, 0, nsm, kWarps) * 4 > 160u * 1024u) nsm--;
     e->nsplit_max = nsm;
     uint32_t cap = (d.max_seq + nsm - 1) / nsm; cap = (cap + 7u) & ~7u; if (cap < 32) cap = 32;
     e->chunk_cap = cap;

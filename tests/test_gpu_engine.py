@@ -225,3 +225,18 @@ def test_rejects_bad_inputs():
     eng.close()
     with pytest.raises(E.NB200Error):
         E.Engine(b"\0" * 4096, 8)           # bad magic
+
+
+def test_few_kv_heads_many_q_heads_shape():
+    """2 kv heads x 8 q heads each, head_dim 128: the attention merge would stage 64 splits x 8 x 128 floats (256 KB) in
+    shared memory; the engine has to bound the split count for such shapes instead of failing to launch."""
+    spec = mf.ModelSpec("wide-gqa", mf.ARCH_QWEN3, 256, 1024, 1, 256, 16, 2, 512, 128)
+    path = mf.cached_model(spec, mf.QUANT_F32, 128)
+    S = 96
+    toks = mf.teacher_tokens(S, spec.vocab)
+    for flags in (E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA, 0):
+        eng = E.Engine(path, S, flags=flags); o = ob.NanoOracle(path, S)
+        for pos in range(S):
+            d = np.abs(eng.forward(toks[pos], pos) - o.forward(toks[pos], pos)).max()
+            assert d <= 1e-4, (flags, pos, d)
+        eng.close(); o.close()
