@@ -264,8 +264,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="run the engine in exact (reference-order) mode")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-mega", action="store_true", help="forbid the persistent megakernel")
-    ap.add_argument("--no-cluster", action="store_true", help="forbid the cluster-resident kernel")
+    ap.add_argument("--no-stream", action="store_true", help="forbid the streaming kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -285,7 +284,7 @@ def main():
     if dist is not None:
         dist.barrier()
     path = mf.cached_model(spec, quant, gs or 128, fast=FAST_FILE.get(args.workload, False))           # every rank finds the file rank 0 wrote
-    flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_MEGA if args.no_mega else 0) | (E.FLAG_NO_CLUSTER if args.no_cluster else 0)
+    flags = (E.FLAG_EXACT if args.exact else 0) | (E.FLAG_NO_PDL if args.no_pdl else 0) | (E.FLAG_NO_GRAPH if args.no_graph else 0) | (E.FLAG_NO_STREAM if args.no_stream else 0)
     tp = args.mode == "tp" and world > 1
     if tp:
         # one rank per process: exchange the CUDA IPC handles of the exchange blocks through torch.distributed
@@ -390,23 +389,21 @@ def main():
     per_gpu_gbs = bytes_tok * (value / world) / 1e9          # replicas: each GPU streams a whole model per token; tp: 1/T of it
     token_roof = {"alg_bytes_per_token": bytes_tok, "achieved_gbs_per_gpu": per_gpu_gbs,
                   "frac_of_peak": per_gpu_gbs / peak, "roofline_tok_s_per_session": peak * 1e9 / bytes_tok * (world if tp else 1)}
-    persistent = eng.path.startswith("cluster") or eng.path.startswith("persistent")
+    persistent = eng.path.startswith("streaming")
     if persistent:
         # the step IS one kernel: a launch decodes n_dec tokens, so the dominant kernel's roofline is the token roofline.
         # per_kernel keeps the phase-by-phase profile of the same device code run as separate launches.
-        kname = "k_decode_cluster" if eng.path.startswith("cluster") else "k_decode_mega"
+        kname = "k_decode_stream"
         launch_us = dec_ms / args.steps * 1e3
         ptraffic = None
         try:
-            ptraffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(
-                args.workload + (":cluster" if kname.endswith("cluster") else ":mega"))
+            ptraffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(args.workload + ":stream")
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": f"{kname} (one launch decodes {n_dec} tokens: all layers + classifier + argmax)",
                 "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak,
                 "traffic": ptraffic * n_dec if ptraffic else None,
-                "traffic_source": (f"ncu --set full capture of one {kname} launch, per-token bytes x {n_dec} tokens, profiles/r1_ncu_full_"
-                                   + ("cluster" if kname.endswith("cluster") else "megakernel") + ".md") if ptraffic else None,
+                "traffic_source": f"ncu --set full capture of one {kname} launch, per-token bytes x {n_dec} tokens, profiles/r2_ncu_full_stream.md" if ptraffic else None,
                 "peak_source": peak_src, "alg_bytes_per_launch": bytes_tok * n_dec,
                 "mean_launch_us": launch_us, "share_of_step": 1.0,
                 "phase_profile_note": "per_kernel = the same phase code launched as separate kernels (graph/PDL off), CUDA events per launch",

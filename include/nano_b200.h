@@ -42,8 +42,7 @@ extern "C" {
 #define NB200_FLAG_EXACT 0x1u      /* exact mode: reference-order fp32 reductions (validation, slower) */
 #define NB200_FLAG_NO_GRAPH 0x2u   /* launch kernels directly instead of replaying a CUDA graph */
 #define NB200_FLAG_NO_PDL 0x4u     /* disable programmatic dependent launch */
-#define NB200_FLAG_NO_MEGA 0x8u    /* use the multi-kernel path instead of the persistent megakernel */
-#define NB200_FLAG_NO_CLUSTER 0x10u /* do not use the cluster-resident kernel (16-CTA cluster, DSMEM activations) */
+#define NB200_FLAG_NO_STREAM 0x10u /* do not use the grid-wide streaming kernel (per-CTA TMA weight ring, one launch per run of tokens) */
 
 /* quantisation / architecture ids: identical to infer/tensor.h:72-76 and infer/infer.h:45-47 */
 #define NB200_QUANT_F32 0x00u

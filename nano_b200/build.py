@@ -35,16 +35,30 @@ def _newer(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
 
 
+# translation units of libnano_b200.so and what each depends on (besides itself)
+UNITS = {
+    "engine.cu": ["kernels.cuh", "expf_ref.cuh", "stream_args.h", "stream_host.h", "../../include/nano_b200.h"],
+    "stream.cu": ["kernels.cuh", "expf_ref.cuh", "stream_args.h", "stream_host.h", "stream.cuh"],
+}
+
+
 def build_engine(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit (compiled in parallel, only when its sources changed), then one link."""
     os.makedirs(LIB, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(ROOT, "include", "nano_b200.h"))
-    if force or _newer(ENGINE_SO, srcs):
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-shared", os.path.join(CSRC, "engine.cu"), "-o", ENGINE_SO]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.run(cmd, check=True)
+    base = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+    if verbose:
+        base.insert(1, "-Xptxas=-v")
+    objs, procs = [], []
+    for unit, deps in UNITS.items():
+        obj = os.path.join(LIB, unit[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [os.path.join(CSRC, unit)] + [os.path.join(CSRC, d) for d in deps]):
+            procs.append((unit, subprocess.Popen(base + ["-c", os.path.join(CSRC, unit), "-o", obj])))
+    failed = [u for u, p in procs if p.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    if procs or _newer(ENGINE_SO, objs):
+        subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", ENGINE_SO] + objs, check=True)
     return ENGINE_SO
 
 

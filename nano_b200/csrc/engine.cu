@@ -27,7 +27,7 @@
 
 #include "../../include/nano_b200.h"
 #include "kernels.cuh"
-#include "cluster.cuh"
+#include "stream_host.h"
 
 using namespace nb;
 
@@ -99,11 +99,13 @@ struct nb200_engine {
     uint32_t nsplit_max = 1, chunk_cap = 32, attn_smem = 0, cls_grid = 1;
     cudaGraphExec_t graph = nullptr;
     bool use_pdl = true;
-    // persistent megakernel (fast mode): one cooperative launch runs n tokens
     unsigned long long *trace_dev = nullptr;
-    // cluster-resident path (cluster.cuh)
-    bool use_cluster = false; const void *cl_kern = nullptr; ClusterArgs cl{}; uint32_t cl_smem = 0;
-    bool use_mega = false; const void *mega_kern = nullptr; uint32_t mega_smem = 0, mega_phase_smem = 0; LayerW *layers_dev = nullptr; unsigned int *bar = nullptr;
+    // grid-wide persistent streaming kernel (stream.cuh): the default path in fast mode on one GPU
+    bool use_stream = false; const void *st_kern = nullptr; StreamArgs sa{}; uint32_t st_smem = 0, st_grid = 0;
+    uint32_t *st_err_host = nullptr, *st_err_dev = nullptr;      // mapped pinned word: the code a device-side spin recorded before trapping
+    uint32_t st_epoch = 0;                                       // exchange epochs handed out so far (stream.cuh)
+    uint64_t stream_bytes = 0;
+    unsigned int *bar = nullptr;
     uint64_t launches = 0, weight_bytes = 0;
     uint32_t launches_per_token = 0;
     std::vector<uint32_t> seen_mirror;   // ids whose seen[] flag is set, by position
@@ -114,7 +116,7 @@ struct nb200_engine {
     bool tied = false;
     // LoRA plug-in (nb200_lora_load): fp32 factors [L][rank][n] / [L][rows][rank] for q, k, v, o; scratch t [4][rank], o1 [E]
     struct Lora { uint32_t rank = 0, alpha = 0; float *a[4] = {}, *b[4] = {}; float *t = nullptr, *o1 = nullptr; bool loaded = false, active = false; } lora;
-    bool path_cluster = false, path_mega = false;     // what the model would run on without a plug-in
+    bool path_stream = false;     // what the model would run on without a plug-in
     unsigned long long *attn_dbg = nullptr;          // NB200_ATTN_DBG=1: %globaltimer stamps of layer L/2's attention kernel
     uint32_t g_H = 0, g_KV = 0, g_q_dim = 0, g_kv_dim = 0;     // whole-model values (== d.* on one GPU)
     unsigned char *tp_block = nullptr; size_t tp_block_bytes = 0;
@@ -388,68 +390,23 @@ int run_token(nb200_engine *e) {
     return run_classifier(e);
 }
 
-typedef void (*MegaKern)(const MegaArgs);
-
-template <int QUANT, int LPG>
-MegaKern pick_mega_kvm(uint32_t kvm) {
-    switch (kvm) {
-        case 1: return k_decode_mega<QUANT, LPG, 1>;
-        case 2: return k_decode_mega<QUANT, LPG, 2>;
-        case 4: return k_decode_mega<QUANT, LPG, 4>;
-        default: return nullptr;
-    }
-}
-
-MegaKern pick_mega(const Dims &d) {
-    if (d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0)) return nullptr;     // in-register half-split RoPE needs hd = 4 * 2^k
-    if (d.quant == 0x00u) return pick_mega_kvm<0x00, 8>(d.kv_mul);
-    if (d.quant == 0x42u) return pick_mega_kvm<0x42, 8>(d.kv_mul);
-    if (d.gs == 128) return pick_mega_kvm<0x80, 8>(d.kv_mul);
-    if (d.gs == 64) return pick_mega_kvm<0x80, 4>(d.kv_mul);
-    return nullptr;
-}
-
-// n_steps tokens in ONE cooperative launch of the persistent kernel
-int launch_mega(nb200_engine *e, uint32_t n_steps) {
+// n_steps tokens in ONE cooperative launch of the streaming kernel
+int launch_stream(nb200_engine *e, uint32_t n_steps) {
     if (n_steps == 0) return 0;
-    MegaArgs g{};
-    g.layers = e->layers_dev;
-    g.cls_w = e->cls.w; g.cls_aux = e->cls.aux; g.emb_w = e->emb.w; g.emb_aux = e->emb.aux;
-    g.g_final = e->norm_final; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
-    g.x = e->x; g.q = e->q; g.kraw = e->kraw; g.xba = e->xba; g.hb = e->hb; g.logits = e->logits;
-    g.ws_m = e->ws_m; g.ws_l = e->ws_l; g.ws_acc = e->ws_acc; g.ticket = e->tickets;
-    g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.cls_val = e->cls_val; g.cls_idx = e->cls_idx;
-    g.bar = e->bar; g.n_steps = n_steps; g.nsplit_max = e->nsplit_max; g.chunk_cap = e->chunk_cap;
-    g.phase_smem = e->mega_phase_smem; g.trace = e->trace_dev;
-    g.dump_codes = e->dump_codes; g.dump_scales = e->dump_scales; g.d = e->d;
+    StreamArgs g = e->sa;
+    g.n_steps = n_steps; g.trace = e->trace_dev;
+    g.epoch_base = e->st_epoch;
+    e->st_epoch += n_steps * 5u * e->d.L;
     CK(cudaMemsetAsync(e->bar, 0, sizeof(unsigned int), e->stream));
     void *params[] = {&g};
-    CK(cudaLaunchCooperativeKernel(e->mega_kern, dim3(e->cls_grid), dim3(kThreads), params, e->mega_smem, e->stream));
-    e->launches++;
-    return 0;
-}
-
-// n_steps tokens in one launch of the 16-CTA cluster kernel
-int launch_cluster(nb200_engine *e, uint32_t n_steps) {
-    if (n_steps == 0) return 0;
-    ClusterArgs g = e->cl;
-    g.n_steps = n_steps; g.trace = e->trace_dev;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(kCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = e->cl_smem; cfg.stream = e->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    void *params[] = {&g};
-    CK(cudaLaunchKernelExC(&cfg, e->cl_kern, params));
+    CK(cudaLaunchCooperativeKernel(e->st_kern, dim3(e->st_grid), dim3(kThreads), params, e->st_smem, e->stream));
     e->launches++;
     return 0;
 }
 
 int launch_token(nb200_engine *e) {
     if (e->tp_size > 1 && !e->tp_attached) return fail(NB200_EINVAL, "tensor-parallel engine: attach the peer ranks first (nb200_tp_attach_*)");
-    if (e->use_cluster) return launch_cluster(e, 1);
-    if (e->use_mega) return launch_mega(e, 1);
+    if (e->use_stream) return launch_stream(e, 1);
     if (e->graph) {
         CK(cudaGraphLaunch(e->graph, e->stream));
         e->launches += e->launches_per_token;
@@ -520,150 +477,140 @@ int put_rows(nb200_engine *e, Mat &m, const uint8_t *w, const uint8_t *aux, uint
     }
 }
 
-// ---------------- cluster-resident path: weight stream + schedule ----------------
-// copy one fused Q80 matrix into the per-rank tile stream: tile = [rows x (n+16) codes, rows padded][rows x gs_stride scales]
-__global__ void k_build_stream(const uint8_t *__restrict__ codes, const float *__restrict__ scales, uint32_t rows_per_rank, uint32_t n, uint32_t G,
-                               uint32_t T, uint32_t tile_stride, uint32_t row_stride, uint32_t gs_stride, uint8_t *stream, uint64_t rank_stride,
-                               uint64_t phase_off) {
-    const uint32_t rank = blockIdx.y;
-    for (uint32_t lrow = blockIdx.x; lrow < rows_per_rank; lrow += gridDim.x) {
-        const uint32_t j = lrow / T, i = lrow % T;
-        const uint32_t rows = min(T, rows_per_rank - j * T);
-        uint8_t *tile = stream + (uint64_t)rank * rank_stride + phase_off + (uint64_t)j * tile_stride;
-        const uint64_t grow = (uint64_t)rank * rows_per_rank + lrow;
-        const int4 *src = reinterpret_cast<const int4 *>(codes + grow * n);
-        int4 *dst = reinterpret_cast<int4 *>(tile + (uint64_t)i * row_stride);
-        for (uint32_t c = threadIdx.x; c < n / 16; c += blockDim.x) dst[c] = src[c];
-        float *sdst = reinterpret_cast<float *>(tile + (uint64_t)rows * row_stride) + (uint64_t)i * gs_stride;
-        for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) sdst[c] = scales[grow * G + c];
-    }
-}
+// ---------------- streaming path: per-CTA tile-ordered weight stream + schedule (stream.cuh) ----------------
+uint32_t env_u32(const char *name, uint32_t dflt) { const char *s = getenv(name); return (s && *s) ? (uint32_t)strtoul(s, nullptr, 10) : dflt; }
 
-typedef void (*ClusterKern)(const ClusterArgs);
-template <int LPG>
-ClusterKern pick_cluster_kvm(uint32_t kvm) {
-    switch (kvm) {
-        case 1: return k_decode_cluster<LPG, 1>;
-        case 2: return k_decode_cluster<LPG, 2>;
-        case 4: return k_decode_cluster<LPG, 4>;
-        default: return nullptr;
-    }
-}
-
-// returns 0 and sets e->use_cluster when the model fits the cluster-resident kernel; 0 without setting it otherwise
-int setup_cluster(nb200_engine *e) {
+// returns 0 and sets e->use_stream when the model fits the streaming kernel; 0 without setting it otherwise
+int setup_stream(nb200_engine *e) {
     const Dims &d = e->d;
-    if (d.quant != 0x80u || d.exact || d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0) || (d.gs != 64 && d.gs != 128) || d.KV > (uint32_t)kCluster || kCluster % d.KV) return 0;
-    ClusterKern k = (d.gs == 128) ? pick_cluster_kvm<8>(d.kv_mul) : pick_cluster_kvm<4>(d.kv_mul);
+    if (d.exact || e->tp_size > 1) return 0;
+    StreamKern k = pick_stream(d);
     if (!k) return 0;
-    const uint32_t L = d.L, E = d.E, QD = d.q_dim, KD = d.kv_dim, F = d.F, V = d.V;
-    struct PM { const Mat *m; uint32_t epi, has_gain, src_sel, layer; };
-    std::vector<PM> pms;
-    for (uint32_t l = 0; l < L; l++) {
-        pms.push_back({&e->qkv[l], (uint32_t)EPI_QKV, 1u, 0u, l});
-        pms.push_back({&e->wo[l], (uint32_t)EPI_RESID, 0u, 1u, l});
-        pms.push_back({&e->w13[l], (uint32_t)EPI_SWIGLU, 1u, 0u, l});
-        pms.push_back({&e->w2[l], (uint32_t)EPI_RESID, 0u, 2u, l});
-    }
-    pms.push_back({&e->cls, (uint32_t)EPI_CLS, 1u, 0u, L});
-    for (auto &pm : pms) if (pm.m->rows % (2 * kCluster) || pm.m->n % 16) return 0;
-    (void)QD; (void)KD; (void)F; (void)V;
+    uint32_t maxn = d.E; if (d.q_dim > maxn) maxn = d.q_dim; if (d.F > maxn) maxn = d.F;
+    if (maxn > st_prep_max_n(d.quant, d.gs)) return 0;
+    if (d.quant == 0x80u && (d.E % 16 || d.q_dim % 16 || d.F % 16)) return 0;
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+    if (!coop) return 0;
+    const uint32_t NC = (uint32_t)e->num_sms;
+    if (d.KV > NC || (d.E + NC - 1) / NC > (uint32_t)kStOwnMax) return 0;
+    const uint32_t L = d.L;
 
-    // stage size and per-phase tile geometry
-    const char *sc_env = getenv("NB200_STAGE_KB");
-    const uint32_t stage_cap = (sc_env ? (uint32_t)atoi(sc_env) : 26u) * 1024u + 512u;
-    uint32_t stage_bytes = (E * 4 + 127) & ~127u;
-    std::vector<ClPhase> ph(pms.size());
-    uint64_t off = 0; uint32_t tile_idx = 0;
-    for (size_t i = 0; i < pms.size(); i++) {
-        const Mat &m = *pms[i].m;
-        const uint32_t G = m.n / d.gs, rpr = m.rows / kCluster, row_stride = m.n + 16u, gs_stride = G | 1u, rowb = row_stride + 4u * gs_stride;
-        uint32_t T = 32; while (T > 2 && T * rowb > stage_cap) T >>= 1;      // one lane per row: 32, 16, 8 ... rows per tile
-        if (T * rowb > stage_cap) return 0;
-        const uint32_t tstride = (T * rowb + 15u) & ~15u;
-        if (tstride > stage_bytes) stage_bytes = (tstride + 127u) & ~127u;
-        ClPhase &c = ph[i];
-        memset(&c, 0, sizeof c);
-        c.stream_off = off; c.has_gain = pms[i].has_gain; c.rows_per_rank = rpr; c.rows_per_tile = T; c.tile_stride = tstride;
-        c.n = m.n; c.epi = pms[i].epi; c.layer = pms[i].layer; c.pad = pms[i].src_sel; c.row_stride = row_stride; c.gs_stride = gs_stride;
-        c.ntiles = (rpr + T - 1) / T;
-        c.tile_base = tile_idx; tile_idx += c.ntiles + (c.has_gain ? 1u : 0u);
-        c.gain_off = (pms[i].epi == EPI_QKV) ? (uint64_t)pms[i].layer * E * 4
-                   : (pms[i].epi == EPI_SWIGLU) ? ((uint64_t)L + pms[i].layer) * E * 4 : (uint64_t)2 * L * E * 4;
-        off += (uint64_t)c.ntiles * tstride;
-        off = (off + 127u) & ~(uint64_t)127u;
-    }
-    const uint64_t rank_stride = off;
-
-    // shared-memory plan
-    auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
-    const uint32_t rpk = kCluster / d.KV;
-    uint32_t lpr = 1; while (lpr * 4 < d.hd) lpr <<= 1;
-    const uint32_t rpw = 32 / lpr;
-    (void)rpw;
-    const uint32_t attn_floats = attn_stream_ws_floats(d.kv_mul, d.hd, kWarps);
-    uint32_t maxn = E; if (d.q_dim > maxn) maxn = d.q_dim; if (d.F > maxn) maxn = d.F;
-    uint32_t o = 0;
-    ClusterArgs &g = e->cl;
+    StreamArgs &g = e->sa;
     memset(&g, 0, sizeof g);
-    g.off_phases = o; o += al((uint32_t)(ph.size() * sizeof(ClPhase)));
-    g.off_x = o; o += al(E * 4); g.off_q = o; o += al(d.q_dim * 4); g.off_kraw = o; o += al(d.kv_dim * 4); g.off_vrow = o; o += al(d.kv_dim * 4);
-    g.off_xba = o; o += al(d.q_dim * 4); g.off_hb = o; o += al(d.F * 4);
-    g.off_part = o; o += al(d.KV * rpk * d.kv_mul * (d.hd + 2) * 4);
-    g.off_act = o; o += al(act_region_bytes(0x80u, maxn, d.gs));
-    g.off_slots = o; o += al(2 * kCluster * 4);
-    g.off_attn = o; o += al(attn_floats * 4);
-    g.off_ring = o;
+    struct KM { uint32_t rows, n, unit; } km[5] = {
+        {d.q_dim + 2 * d.kv_dim, d.E, 1}, {d.E, d.q_dim, 1}, {2 * d.F, d.E, 2}, {d.E, d.F, 1}, {d.V, d.E, 1}};
+    uint32_t main_b[5], aux_b[5], unit_b_max = 0;
+    for (int i = 0; i < 5; i++) {
+        const uint32_t n = km[i].n;
+        main_b[i] = (d.quant == 0x00u) ? n * 4u : (d.quant == 0x80u) ? n : n / 2u;
+        aux_b[i] = (d.quant == 0x00u) ? 0u : (d.quant == 0x80u) ? (n / d.gs) * 4u : (n / 256u) * 20u;
+        StKind &sk = g.kind[i];
+        sk.units = km[i].rows / km[i].unit; sk.unit_rows = km[i].unit; sk.n = n;
+        sk.row_stride = main_b[i] + 16u;
+        sk.aux_stride = (d.quant == 0x80u) ? ((n / d.gs) | 1u) * 4u : aux_b[i];
+        const uint32_t ub = km[i].unit * (sk.row_stride + sk.aux_stride);
+        if (ub > unit_b_max) unit_b_max = ub;
+    }
+    // ring stage: at least two row units of the longest row, 16 KB by default
+    uint32_t stage_bytes = env_u32("NB200_STAGE_KB", 16) * 1024u;
+    if (stage_bytes < 2 * unit_b_max + 16u) stage_bytes = (2 * unit_b_max + 16u + 1023u) & ~1023u;
+    uint32_t kv_rows = (stage_bytes / (2u * d.hd * 4u)) & ~7u;
+    if (kv_rows < 8) return 0;
+    uint64_t off = 0;
+    uint32_t ntl[5];
+    for (int i = 0; i < 5; i++) {
+        StKind &sk = g.kind[i];
+        const uint32_t rowb = sk.row_stride + sk.aux_stride;
+        const uint32_t max_rows = ((sk.units + NC - 1) / NC) * sk.unit_rows;
+        uint32_t T = (stage_bytes - 16u) / rowb;
+        T -= T % sk.unit_rows;
+        if (T > max_rows) T = max_rows;
+        if (T < sk.unit_rows) return 0;
+        sk.tile_rows = T;
+        sk.tile_stride = (T * rowb + 15u) & ~15u;
+        ntl[i] = (max_rows + T - 1) / T;
+        if (i == SK_CLS) off = 0;
+        sk.off = off;
+        off += (uint64_t)ntl[i] * sk.tile_stride;
+        off = (off + 127u) & ~(uint64_t)127u;
+        if (i == SK_W2) g.layer_stride = off;
+    }
+    g.cls_off = (uint64_t)L * g.layer_stride;
+    g.kind[SK_CLS].off = 0;
+    g.cta_stride = (g.cls_off + (uint64_t)ntl[SK_CLS] * g.kind[SK_CLS].tile_stride + 127u) & ~(uint64_t)127u;
+
+    // shared-memory plan: [activation operand | embedding row] aliased with the attention workspace, then the ring
+    auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
+    const uint32_t nsplit_max = e->nsplit_max;          // num_sms / kv heads (<= 64), as the multi-kernel path
+    const uint32_t act_b = al(act_region_bytes(d.quant, maxn, d.gs ? d.gs : 1));
+    uint32_t region0 = act_b + al(d.E * 4u);
+    const uint32_t attn_b = al(st_attn_smem_floats(d.kv_mul, d.hd, nsplit_max, (uint32_t)kStSegTiles * kv_rows) * 4u);
+    if (attn_b > region0) region0 = attn_b;
+    g.off_act = 0; g.off_xs = act_b; g.off_attn = 0; g.off_ring = region0;
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
-    const uint32_t static_smem = 2048;
-    if ((uint32_t)max_optin < o + static_smem + 2 * stage_bytes) return 0;
-    uint32_t nst = ((uint32_t)max_optin - static_smem - o) / stage_bytes;
-    if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
-    if (nst < 2) return 0;
-    const uint32_t smem = o + nst * stage_bytes;
-
+    const uint32_t static_smem = 6144;                  // mbarriers, row ranges, residual rows, reduction scratch (static __shared__)
+    if ((uint32_t)max_optin < region0 + static_smem + 3 * stage_bytes) return 0;
+    uint32_t nst = ((uint32_t)max_optin - static_smem - region0) / stage_bytes;
+    const uint32_t nst_cap = env_u32("NB200_STAGES", kStMaxStages);
+    if (nst > nst_cap) nst = nst_cap;
+    if (nst > (uint32_t)kStMaxStages) nst = kStMaxStages;
+    if (nst < 2u * (uint32_t)kStSegTiles) return 0;      // an attention segment keeps kStSegTiles tiles resident while the next ones arrive
+    const uint32_t smem = region0 + nst * stage_bytes;
     cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (ce != cudaSuccess) { cudaGetLastError(); return 0; }
-    {   // can one 16-CTA cluster be resident?
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(kCluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        int ncl = 0;
-        ce = cudaOccupancyMaxActiveClusters(&ncl, (const void *)k, &cfg);
-        if (ce != cudaSuccess || ncl < 1) { cudaGetLastError(); return 0; }
-    }
+    int occ = 0;
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)k, kThreads, smem);
+    if (ce != cudaSuccess || occ < 1) { cudaGetLastError(); return 0; }
 
-    // device objects: stream, shared gains, phase table
-    uint8_t *stream = nullptr; float *gains = nullptr; ClPhase *phd = nullptr;
-    DM(stream, rank_stride * kCluster + 256);
-    DM(gains, ((size_t)2 * L + 1) * E * 4 + 256);
-    DM(phd, ph.size() * sizeof(ClPhase));
-    CK(cudaMemcpy(gains, e->norm_attn, (size_t)L * E * 4, cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(gains + (size_t)L * E, e->norm_ffn, (size_t)L * E * 4, cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(gains + (size_t)2 * L * E, e->norm_final, (size_t)E * 4, cudaMemcpyDeviceToDevice));
-    CK(cudaMemcpy(phd, ph.data(), ph.size() * sizeof(ClPhase), cudaMemcpyHostToDevice));
-    CK(cudaMemset(stream, 0, rank_stride * kCluster + 256));
-    for (size_t i = 0; i < pms.size(); i++) {
-        const Mat &m = *pms[i].m;
-        const ClPhase &c = ph[i];
-        uint32_t gx = c.rows_per_rank < 1024 ? c.rows_per_rank : 1024;
-        k_build_stream<<<dim3(gx, kCluster), 128>>>((const uint8_t *)m.w, (const float *)m.aux, c.rows_per_rank, m.n, m.n / d.gs, c.rows_per_tile,
-                                                  c.tile_stride, c.row_stride, c.gs_stride, stream, rank_stride, c.stream_off);
-        CK(cudaGetLastError());
+    // device objects: the stream copy of the weights
+    uint8_t *stream = nullptr;
+    const uint64_t total = g.cta_stride * NC + 256;
+    DM(stream, total);
+    CK(cudaMemset(stream, 0, total));
+    auto build = [&](int ki, const Mat &m, uint64_t base_off) -> int {
+        const StKind &sk = g.kind[ki];
+        uint32_t gx = ((sk.units + NC - 1) / NC) * sk.unit_rows; if (gx > 1024) gx = 1024; if (gx < 1) gx = 1;
+        CK(stream_build_launch((const uint8_t *)m.w, (const uint8_t *)m.aux, main_b[ki], aux_b[ki], sk, stream, g.cta_stride, base_off, gx, NC));
+        return 0;
+    };
+    int r;
+    for (uint32_t l = 0; l < L; l++) {
+        const uint64_t lb = (uint64_t)l * g.layer_stride;
+        if ((r = build(SK_QKV, e->qkv[l], lb)) || (r = build(SK_O, e->wo[l], lb)) || (r = build(SK_W13, e->w13[l], lb)) || (r = build(SK_W2, e->w2[l], lb))) return r;
     }
+    if ((r = build(SK_CLS, e->cls, g.cls_off))) return r;
     CK(cudaDeviceSynchronize());
-    e->weight_bytes += rank_stride * kCluster;
+    e->stream_bytes = total;
 
-    g.stream = stream; g.rank_stride = rank_stride; g.shared_base = (const uint8_t *)gains; g.phases = phd;
-    g.nphases = (uint32_t)ph.size(); g.tiles_per_token = tile_idx; g.nstages = nst; g.stage_bytes = stage_bytes;
-    g.emb_w = e->emb.w; g.emb_aux = e->emb.aux; g.logits = e->logits; g.kc = e->kc; g.vc = e->vc;
+    if (!e->bar) { DM(e->bar, 64); CK(cudaMemset(e->bar, 0, 64)); }
+    CK(cudaHostAlloc(&e->st_err_host, 64, cudaHostAllocMapped));
+    memset(e->st_err_host, 0, 64);
+    CK(cudaHostGetDevicePointer((void **)&e->st_err_dev, e->st_err_host, 0));
+
+    g.stream = stream; g.nstages = nst; g.stage_bytes = stage_bytes; g.kv_tile_rows = kv_rows;
+    g.g_attn = e->norm_attn; g.g_ffn = e->norm_ffn; g.g_final = e->norm_final;
     g.qnorm = e->qnorm; g.knorm = e->knorm; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
-    g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.n_steps = 1; g.d = d;
-    e->cl_kern = (const void *)k; e->cl_smem = smem; e->use_cluster = true; e->launches_per_token = 1;
+    g.emb_w = e->emb.w; g.emb_aux = e->emb.aux;
+    g.logits = e->logits; g.kc = e->kc; g.vc = e->vc;
+    {   // activation exchange words {value, epoch}, zeroed once: epoch 0 is never handed out
+        auto words = [&](unsigned long long *&p, size_t n) -> int { DM(p, n * 8 + 256); CK(cudaMemset(p, 0, n * 8 + 256)); return 0; };
+        const uint32_t ns[3] = {d.E, d.q_dim, d.F};
+        if ((r = words(g.xq, (size_t)d.q_dim + 2 * d.kv_dim))) return r;
+        for (int i = 0; i < 3; i++) {
+            g.rs[i] = ((ns[i] + 31u) & ~31u) + 32u;                 // replicas 256 bytes apart at least: different L2 slices
+            if ((r = words(g.xv[i], (size_t)g.rs[i] * kStRep))) return r;
+        }
+        if ((r = words(g.xws, (size_t)d.KV * nsplit_max * d.kv_mul * (d.hd + 2)))) return r;
+    }
+    g.cls_val = e->cls_val; g.cls_idx = e->cls_idx;
+    g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.bar = e->bar; g.err = e->st_err_dev;
+    g.n_steps = 1; g.nsplit_max = nsplit_max;
+    uint32_t ct = 65536u / (d.hd * 8u); ct &= ~7u; if (ct < 32) ct = 32;
+    g.chunk_target = env_u32("NB200_ATTN_CHUNK", ct);
+    if (g.chunk_target < 8) g.chunk_target = 8;
+    g.d = d;
+    e->st_kern = (const void *)k; e->st_smem = smem; e->st_grid = NC; e->use_stream = true; e->launches_per_token = 1;
     return 0;
 }
 
@@ -911,16 +858,8 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     DM(e->kc, kv_floats * 4); DM(e->vc, kv_floats * 4);
     CK(cudaMemset(e->kc, 0, kv_floats * 4)); CK(cudaMemset(e->vc, 0, kv_floats * 4));   // calloc'd in the reference (infer.c:47)
     CK(cudaMemset(e->x, 0, E * 4)); CK(cudaMemset(e->logits, 0, V * 4));
-    const char *mega_env = getenv("NB200_MEGA");
-    // Default execution path, from the round-1 measurements on B200 (profiles/r1_paths.md): the cluster-resident kernel wins
-    // for small Q80 models, the CUDA-graph multi-kernel path for larger Q80 models, the persistent megakernel for F32/Q4K.
-    // NB200_MEGA=1 / NB200_CLUSTER=1 force a path, =0 forbids it.
-    const bool mega_forced = mega_env && atoi(mega_env) == 1;
-    const bool mega_default = (d.quant != 0x80u);
-    MegaKern mk = (T > 1 || d.exact || (flags & NB200_FLAG_NO_MEGA) || (mega_env && atoi(mega_env) == 0) || !(mega_default || mega_forced)) ? nullptr : pick_mega(d);
-    int coop = 0;
-    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-    if (!coop) mk = nullptr;
+    // Execution paths: the streaming kernel (stream.cuh) is the default in fast mode on one GPU; the CUDA-graph multi-kernel
+    // path serves exact mode, tensor parallelism, LoRA and shapes the streaming kernel does not take.
     uint32_t nsm = (uint32_t)e->num_sms / e->g_KV;  // (kv head, split) items <= one per SM; same split in every path and TP size => identical bits
     if (nsm < 1) nsm = 1; if (nsm > 64) nsm = 64;
     // the merging CTA stages nsplit x kv_mul x head_dim partial accumulators in shared memory: keep that under 160 KB
@@ -948,44 +887,12 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     memset(e->st_host, 0, sizeof(DevState));
     CK(cudaDeviceSynchronize());
 
-    if (mk) {
-        // persistent kernel: dynamic smem = largest phase (activation prep of n in {E, q_dim, F}; attention item)
-        uint32_t sm = attn_fast_smem_floats(d.kv_mul, d.hd, e->chunk_cap, e->nsplit_max, kWarps) * 4u;
-        const uint32_t ns[3] = {d.E, d.q_dim, d.F};
-        for (uint32_t n : ns) { const uint32_t b = act_smem_bytes(d.quant, n, d.gs ? d.gs : 1); if (b > sm) sm = b; }
-        sm = (sm + 15u) & ~15u;
-        e->mega_phase_smem = sm;
-        sm += (uint32_t)(L * sizeof(LayerW));
-        int occ = 0;
-        cudaError_t ce = cudaFuncSetAttribute((const void *)mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)mk, kThreads, sm);
-        if (ce == cudaSuccess && occ >= 1) {
-            std::vector<LayerW> lw(L);
-            const size_t kvl = (size_t)d.KV * d.max_seq * d.hd;
-            for (uint64_t l = 0; l < L; l++) {
-                lw[l].qkv_w = e->qkv[l].w; lw[l].qkv_aux = e->qkv[l].aux; lw[l].wo_w = e->wo[l].w; lw[l].wo_aux = e->wo[l].aux;
-                lw[l].w13_w = e->w13[l].w; lw[l].w13_aux = e->w13[l].aux; lw[l].w2_w = e->w2[l].w; lw[l].w2_aux = e->w2[l].aux;
-                lw[l].g_attn = e->norm_attn + l * E; lw[l].g_ffn = e->norm_ffn + l * E;
-                lw[l].qnorm = e->qnorm ? e->qnorm + l * d.hd : nullptr; lw[l].knorm = e->knorm ? e->knorm + l * d.hd : nullptr;
-                lw[l].kc = e->kc + l * kvl; lw[l].vc = e->vc + l * kvl;
-            }
-            DM(e->layers_dev, L * sizeof(LayerW));
-            CK(cudaMemcpy(e->layers_dev, lw.data(), L * sizeof(LayerW), cudaMemcpyHostToDevice));
-            DM(e->bar, 64); CK(cudaMemset(e->bar, 0, 64));
-            e->mega_kern = (const void *)mk; e->mega_smem = sm; e->use_mega = true;
-            e->launches_per_token = 1;
-        } else {
-            cudaGetLastError();
-        }
-    }
     {
-        const char *cl_env = getenv("NB200_CLUSTER");
-        const bool cl_forced = cl_env && atoi(cl_env) == 1;
-        const bool cl_default = e->weight_bytes < (256ull << 20);          // small models are latency-bound: keep activations on-chip
-        if (T == 1 && !(flags & NB200_FLAG_NO_CLUSTER) && !(cl_env && atoi(cl_env) == 0) && (cl_default || cl_forced)) { if ((r = setup_cluster(e))) return r; }
-        if (e->use_cluster) e->use_mega = false;
+        // Default path in fast mode on one GPU: the grid-wide streaming kernel.  NB200_STREAM=0 / NB200_FLAG_NO_STREAM forbid it.
+        const char *st_env = getenv("NB200_STREAM");
+        if (T == 1 && !(flags & NB200_FLAG_NO_STREAM) && !(st_env && atoi(st_env) == 0)) { if ((r = setup_stream(e))) return r; }
     }
-    e->path_cluster = e->use_cluster; e->path_mega = e->use_mega;
+    e->path_stream = e->use_stream;
     if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
     guard.ok = true;
     *out = e;
@@ -994,7 +901,7 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
 
 static int finish_paths(nb200_engine *e) {
     int r = 0;
-    if (e->use_mega || e->use_cluster) {
+    if (e->use_stream) {
         // nothing to capture: a token (or a whole run of tokens) is one launch
     } else if (!(e->flags & NB200_FLAG_NO_GRAPH)) {
         r = capture_graph(e);
@@ -1026,9 +933,8 @@ static int lora_set_active(nb200_engine *e, bool on) {
     CK(cudaStreamSynchronize(e->stream));
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     e->lora.active = on;
-    e->use_cluster = on ? false : e->path_cluster;
-    e->use_mega = on ? false : e->path_mega;
-    e->launches_per_token = (e->use_cluster || e->use_mega) ? 1u : 0u;
+    e->use_stream = on ? false : e->path_stream;
+    e->launches_per_token = e->use_stream ? 1u : 0u;
     return finish_paths(e);
 }
 
@@ -1139,7 +1045,7 @@ int nb200_get_config(const nb200_engine *e, nb200_config *c) {
     c->block_size = d.block_size; c->vocab_size = d.V; c->n_layer = d.L; c->n_embd = d.E;
     c->n_head = e->g_H; c->n_kv_head = e->g_KV; c->n_hidden = d.F; c->tied = e->tied ? 1u : 0u; c->head_dim = d.hd;
     c->q_dim = e->g_q_dim; c->kv_dim = e->g_kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
-    c->reserved[0] = e->use_cluster ? 3u : e->use_mega ? 2u : (e->graph ? 1u : 0u);      // execution path: 3 cluster, 2 megakernel, 1 graph, 0 direct launches
+    c->reserved[0] = e->use_stream ? 4u : (e->graph ? 1u : 0u);      // execution path: 4 streaming kernel, 1 graph, 0 direct launches
     return 0;
 }
 
@@ -1228,12 +1134,10 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
     e->seen_valid = false; e->seen_mirror.clear();
     CK(cudaEventRecord(ev[0], e->stream));
-    if (e->use_cluster) { if ((r = launch_cluster(e, n_prompt - 1))) return r; }
-    else if (e->use_mega) { if ((r = launch_mega(e, n_prompt - 1))) return r; }
+    if (e->use_stream) { if ((r = launch_stream(e, n_prompt - 1))) return r; }
     else for (uint32_t p = 0; p + 1 < n_prompt; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[1], e->stream));
-    if (e->use_cluster) { if ((r = launch_cluster(e, n_total - n_prompt))) return r; }
-    else if (e->use_mega) { if ((r = launch_mega(e, n_total - n_prompt))) return r; }
+    if (e->use_stream) { if ((r = launch_stream(e, n_total - n_prompt))) return r; }
     else for (uint32_t p = n_prompt - 1; p + 1 < n_total; p++) if ((r = launch_token(e))) return r;
     CK(cudaEventRecord(ev[2], e->stream));
     CK(cudaMemcpyAsync(ids, e->ids_dev, (size_t)n_total * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -1338,16 +1242,16 @@ int nb200_read_attn_trace(nb200_engine *e, unsigned long long *stamps32) {
 // Debug: per-barrier clock64() stamps of CTA 0 for one token through the persistent kernel (5L+3 stamps + 1).
 int nb200_trace_token(nb200_engine *e, uint32_t token, uint32_t pos, unsigned long long *stamps, uint32_t cap, uint32_t *count) {
     if (!e || !stamps || !count) return fail(NB200_EINVAL, "null argument");
-    if (!e->use_mega && !e->use_cluster) return fail(NB200_EINVAL, "persistent kernel not active");
+    if (!e->use_stream) return fail(NB200_EINVAL, "persistent kernel not active");
     CK(cudaSetDevice(e->device));
-    const uint32_t n = 1024 + 64;          // [0, 5L+4): per-barrier stamps; [1024, 1024+48): intra-phase stamps of layer L/2
+    const uint32_t n = 1024 + 256;         // [0, 5L+2): per-barrier stamps; [1024, 1024+15): phase stamps of layer L/2; [1100, 1100+64): stamps inside its four matvec phases
     if (cap < n || 5 * e->d.L + 4 > 1024) return fail(NB200_EINVAL, "need room for %u stamps", n);
     unsigned long long *buf = nullptr;
     CK(cudaMalloc(&buf, (size_t)n * 8));
     CK(cudaMemset(buf, 0, (size_t)n * 8));
     e->trace_dev = buf;
     int r = push_state(e, pos, 1, 0, 0, 1.0f, token, 1);
-    if (!r) r = e->use_cluster ? launch_cluster(e, 1) : launch_mega(e, 1);
+    if (!r) r = launch_stream(e, 1);
     e->trace_dev = nullptr;
     cudaStreamSynchronize(e->stream);
     if (!r) { CK(cudaMemcpy(stamps, buf, (size_t)n * 8, cudaMemcpyDeviceToHost)); *count = n; }

@@ -23,6 +23,11 @@
 
 #include "expf_ref.cuh"
 
+// Non-template kernels get internal linkage in translation units that only want the device helpers (stream.cu).
+#ifndef NB_K
+#define NB_K
+#endif
+
 namespace nb {
 
 constexpr int kThreads = 512;            // matvec CTA: 16 warps
@@ -321,10 +326,11 @@ __device__ void prep_f32(const float *src, const float *__restrict__ gain, int n
 // (int8) round(x / scale) of tensor.c:40-42, bit-exact with a fast path: q = x * (1/scale) is within ~4e-5 of the
 // correctly rounded quotient for |q| <= 127, so unless q sits within 1e-3 of a .5 boundary the rounded integer is
 // unambiguous; the rare boundary case takes the IEEE division + roundf path.
+static __device__ __noinline__ int q80_code_slow(float v, float sc) { return (int)roundf(__fdiv_rn(v, sc)); }   // rare: kept out of line
 __device__ __forceinline__ int q80_code(float v, float sc, float rinv) {
     const float q = v * rinv;
     const float a = fabsf(q), fl = floorf(a), frac = a - fl;
-    if (fabsf(frac - 0.5f) < 1e-3f) return (int)roundf(__fdiv_rn(v, sc));
+    if (fabsf(frac - 0.5f) < 1e-3f) return q80_code_slow(v, sc);
     const int c = (int)fl + (frac > 0.5f ? 1 : 0);
     return q < 0.0f ? -c : c;
 }
@@ -449,7 +455,7 @@ __device__ void prep_q4k(const float *src, const float *__restrict__ gain, int n
 // quantize_tensor_q4k_in_situ (tensor.c:281-310) for whole tensors whose last dimension is a multiple of 256: every
 // 256-element block is independent, one warp per block, output in the reference's 160-byte block layout
 // {u32 tag=0x42, u32 len=256, u32 meta=0, f32 s_scale, f32 s_bias, u8 sb[12], u8 value[128]} (tensor.h:96-114).
-__global__ void __launch_bounds__(256) k_q4k_quantize_blocks(const float *__restrict__ x, unsigned long long nblocks, uint8_t *__restrict__ blocks) {
+NB_K __global__ void __launch_bounds__(256) k_q4k_quantize_blocks(const float *__restrict__ x, unsigned long long nblocks, uint8_t *__restrict__ blocks) {
     const int lane = threadIdx.x & 31;
     const unsigned long long w0 = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (unsigned long long)gridDim.x * 8;
     for (unsigned long long b = w0; b < nblocks; b += nw) {
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(256) k_q4k_quantize_blocks(const float *__rest
 // matmul_q4k (tensor.c:438-471) on the reference's own block layout for BOTH operands (x already quantised by the caller):
 // one warp per row, lane = (block of the 4-block step, group); dot_two_blocks_q4k's integer sums with dp4a, its 4-term
 // fp32 expression left to right, groups then blocks accumulated in the reference's order.
-__global__ void __launch_bounds__(256) k_q4k_matvec_blocks(const uint8_t *__restrict__ wblocks, const uint8_t *__restrict__ xblocks,
+NB_K __global__ void __launch_bounds__(256) k_q4k_matvec_blocks(const uint8_t *__restrict__ wblocks, const uint8_t *__restrict__ xblocks,
                                                            uint32_t rows, uint32_t bpr, float *__restrict__ out) {
     const int lane = threadIdx.x & 31, gi = lane & 7, j = gi & 3;
     const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1021,7 +1027,7 @@ struct LoraAArgs {
     float *t;                               // out [nmat][rank]
     uint32_t exact;
 };
-__global__ void __launch_bounds__(kThreads) k_lora_a(const LoraAArgs a) {
+NB_K __global__ void __launch_bounds__(kThreads) k_lora_a(const LoraAArgs a) {
     extern __shared__ __align__(16) unsigned char act[];
     __shared__ float red[32];
     pdl_launch_dependents();
@@ -1053,7 +1059,7 @@ struct LoraBArgs {
     uint32_t store;                         // 1: dst[0][i] = y (o site);  0: dst += y
     const DevState *st; Dims d;
 };
-__global__ void __launch_bounds__(256) k_lora_b(const LoraBArgs a) {
+NB_K __global__ void __launch_bounds__(256) k_lora_b(const LoraBArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     uint32_t i = blockIdx.x * 256 + threadIdx.x, m = 0;
@@ -1081,7 +1087,7 @@ struct EmbedArgs {
     uint32_t ll;                        // tensor parallel: x is a vector of {value, epoch} words (epoch unused for the local embedding)
 };
 
-__global__ void __launch_bounds__(256) k_embed(const EmbedArgs a) {
+NB_K __global__ void __launch_bounds__(256) k_embed(const EmbedArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     const Dims &d = a.d;
@@ -1517,7 +1523,7 @@ __global__ void __launch_bounds__(kThreads) k_attention_fast(const AttnArgs a) {
     attn_item<KVM, kThreads, TP>(a, blockIdx.y, blockIdx.x, pos, range, chunk, nsplit, sm, is_last);
 }
 
-__global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {
+NB_K __global__ void __launch_bounds__(kAttnThreads) k_attention(const AttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
     __shared__ uint32_t is_last;
@@ -1666,7 +1672,7 @@ struct AttnExactArgs {
     float *xba; float *att; const DevState *st; Dims d;
 };
 
-__global__ void __launch_bounds__(kAttnThreads) k_attention_exact(const AttnExactArgs a) {
+NB_K __global__ void __launch_bounds__(kAttnThreads) k_attention_exact(const AttnExactArgs a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
     pdl_launch_dependents();
@@ -1721,7 +1727,7 @@ __global__ void __launch_bounds__(kAttnThreads) k_attention_exact(const AttnExac
 // penalty + first-max argmax + state update over logits already in HBM (exact-mode F32 classifier)
 struct FinalizeArgs { float *logits; uint32_t V; const uint8_t *seen; uint8_t *seen_rw; uint32_t *ids; DevState *st; };
 
-__global__ void __launch_bounds__(1024) k_cls_finalize(const FinalizeArgs a) {
+NB_K __global__ void __launch_bounds__(1024) k_cls_finalize(const FinalizeArgs a) {
     float *logits = a.logits; const uint32_t V = a.V; const uint8_t *seen = a.seen; uint8_t *seen_rw = a.seen_rw;
     uint32_t *ids = a.ids; DevState *st = a.st;
     __shared__ float bvs[32];
@@ -1757,12 +1763,12 @@ __global__ void __launch_bounds__(1024) k_cls_finalize(const FinalizeArgs a) {
 }
 
 // marks seen[ids[i]] for i in [lo, hi) (repetition-penalty bookkeeping in API mode)
-__global__ void k_mark_seen(uint8_t *seen, const uint32_t *ids, uint32_t lo, uint32_t hi) {
+NB_K __global__ void k_mark_seen(uint8_t *seen, const uint32_t *ids, uint32_t lo, uint32_t hi) {
     for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) seen[ids[i]] = 1;
 }
 
 // standalone prep kernels for the op-level C-ABI (same device functions as the fused prologues)
-__global__ void __launch_bounds__(kThreads) k_op_prep(const float *src, const float *gain, uint32_t n, uint32_t gs, uint32_t quant,
+NB_K __global__ void __launch_bounds__(kThreads) k_op_prep(const float *src, const float *gain, uint32_t n, uint32_t gs, uint32_t quant,
                                                      uint32_t exact, float *out_f32, int8_t *dump_codes, float *dump_scales) {
     extern __shared__ __align__(16) unsigned char act[];
     __shared__ float red[32];
@@ -1774,54 +1780,11 @@ __global__ void __launch_bounds__(kThreads) k_op_prep(const float *src, const fl
     else prep_q4k<kThreads>(src, gain, n, exact != 0, act, stage, red, dump_codes, dump_scales);
 }
 
-// ================================================================================================
-// Persistent decode megakernel.
-//
-// At batch 1 the path is latency-bound, not bandwidth-bound: a Nano-168M layer is 6.7 MB (~1 us of HBM
-// time) but needs five grid-wide dependencies (QKV -> attention -> O -> W1|W3 -> W2).  Measured on B200,
-// a kernel boundary costs ~6-7 us even inside a CUDA graph with PDL, i.e. ~800 us/token for 122 launches.
-// k_decode_mega keeps one CTA per SM resident for a whole run of tokens and replaces every kernel boundary
-// with a ~1 us counter barrier in L2; while a CTA waits it has already prefetched the next phase's weight
-// rows into L2.  The phases are the same device functions the multi-kernel path launches, so the arithmetic
-// (and the parity results) are identical.
-// ================================================================================================
-struct LayerW {
-    const void *qkv_w, *qkv_aux, *wo_w, *wo_aux, *w13_w, *w13_aux, *w2_w, *w2_aux;
-    const float *g_attn, *g_ffn, *qnorm, *knorm;
-    float *kc, *vc;
-};
-
-struct MegaArgs {
-    const LayerW *layers;               // [L] in HBM (immutable)
-    const void *cls_w, *cls_aux, *emb_w, *emb_aux;
-    const float *g_final, *rope_cos, *rope_sin;
-    float *x, *q, *kraw, *xba, *hb, *logits;
-    float *ws_m, *ws_l, *ws_acc; uint32_t *ticket;
-    DevState *st; uint32_t *ids; uint8_t *seen; float *cls_val; uint32_t *cls_idx;
-    unsigned int *bar;                  // grid barrier counter (zeroed by the host before every launch)
-    uint32_t n_steps, nsplit_max, chunk_cap;
-    uint32_t phase_smem;                // bytes of dynamic smem used by the phases; the layer table follows
-    unsigned long long *trace;          // optional: CTA 0 stamps clock64() after every barrier of the LAST step
-    int8_t *dump_codes; float *dump_scales;
-    Dims d;
-};
-
+// helpers shared with the persistent streaming kernel (stream.cuh)
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-
-// Monotonic counter barrier across the persistent grid (all CTAs co-resident: cooperative launch).
-__device__ __forceinline__ void grid_barrier(unsigned int *ctr, volatile unsigned int &target_smem, uint32_t ncta) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int target = target_smem + ncta;      // lives in shared memory: every poll invalidates L1, so a
-        target_smem = target;                                // spilled register would cost an L2 round trip per barrier
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");   // release: this CTA's phase outputs
-        while (ld_acquire_u32(ctr) < target) { }
-    }
-    __syncthreads();
 }
 
 // embedding row -> x (infer.c:987-988 + load-time dequantisation), by one CTA
@@ -1848,129 +1811,6 @@ __device__ __forceinline__ void embed_row(const void *w, const void *aux, float 
         }
         x[i] = v;
     }
-}
-
-template <int QUANT, int LPG, int KVM>
-__global__ void __launch_bounds__(kThreads, 1) k_decode_mega(const MegaArgs g) {
-    extern __shared__ __align__(16) unsigned char dsm[];
-    __shared__ MatvecSmem ms;
-    __shared__ uint32_t attn_flag;
-    __shared__ unsigned int target;
-    __shared__ uint32_t ti;
-    constexpr int RBL = 2, RBC = 2;                 // rows per warp task: layer matrices / classifier
-    const uint32_t cta = blockIdx.x, ncta = gridDim.x;
-    const Dims &d = g.d;
-    if (threadIdx.x == 0) { target = 0; ti = 0; }
-
-    // The per-layer pointer table lives in shared memory: every grid barrier invalidates L1 (CCTL.IVALL), so a
-    // table left in HBM costs a chain of dependent L2 round trips at the start of every phase.
-    LayerW *lws = reinterpret_cast<LayerW *>(dsm + g.phase_smem);
-    {
-        const uint64_t *src = reinterpret_cast<const uint64_t *>(g.layers);
-        uint64_t *dst = reinterpret_cast<uint64_t *>(lws);
-        for (uint32_t i = threadIdx.x; i < d.L * (uint32_t)(sizeof(LayerW) / 8); i += kThreads) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-
-    if (cta == 0) {
-        const uint32_t p0 = __ldcg(&g.st->pos);
-        const uint32_t tok = __ldcg(&g.st->use_token) ? __ldcg(&g.st->token) : __ldcg(g.ids + p0);
-        embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, tok, d);
-    }
-    // L2 prefetch of a later phase's weight rows (+ scales / side records, + rmsnorm gain), issued before a barrier
-    auto pf = [&](const void *w, const void *aux, uint32_t rows, uint32_t n, const float *gain) {
-        const uint32_t arb = (QUANT == 0x80) ? (n / (LPG * 16u)) * 4u : (QUANT == 0x42) ? (n / 256u) * 20u : 0u;
-        prefetch_row_blocks<QUANT, RBL>(w, rows, n, cta, ncta, 8, aux, arb, gain);
-    };
-    pf(lws[0].qkv_w, lws[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[0].g_attn);
-    grid_barrier(g.bar, target, ncta);
-
-#define NB_TRACE() do { if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64(); } while (0)
-    for (uint32_t step = 0; step < g.n_steps; step++) {
-        if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps) g.trace[ti++] = clock64();
-        const uint32_t pos = __ldcg(&g.st->pos);
-        const float pen = __ldcg(&g.st->penalty);
-        const uint32_t range = __ldcg(&g.st->is_causal) ? pos + 1 : d.max_seq;
-        uint32_t chunk = (range + g.nsplit_max - 1) / g.nsplit_max;
-        chunk = max(chunk, 32u);
-        chunk = min((chunk + 7u) & ~7u, g.chunk_cap);
-        const uint32_t nsplit = (range + chunk - 1) / chunk;
-
-        for (uint32_t l = 0; l < d.L; l++) {
-            const LayerW &lw = lws[l];
-            MatvecArgs a{};
-            a.d = d; a.st = g.st; a.state_known = 1; a.pos_val = pos; a.pen_val = pen;
-            unsigned long long *dbg = (g.trace && l == d.L / 2 && step + 1 == g.n_steps) ? g.trace + 1024 : nullptr;
-            a.dbg = dbg;
-            // ---- P1: rmsnorm + quantise + QKV + V store ----
-            a.w = lw.qkv_w; a.w_aux = lw.qkv_aux; a.rows = d.q_dim + 2 * d.kv_dim; a.n = d.E;
-            a.src = g.x; a.gain = lw.g_attn; a.out = g.q; a.out_k = g.kraw; a.out_v = lw.vc;
-            a.dump_codes = g.dump_codes; a.dump_scales = g.dump_scales;
-            matvec_phase<QUANT, EPI_QKV, RBL, LPG>(a, cta, ncta, dsm, ms);
-            NB_STAMP(dbg, 6);
-            pf(lw.wo_w, lw.wo_aux, d.E, d.q_dim, nullptr);
-            if (cta < d.KV * nsplit) {          // the K/V chunk of this CTA's attention item (old rows: already final)
-                const uint32_t ag = cta / nsplit, as = cta % nsplit;
-                const uint32_t t0 = as * chunk, t1 = min(range, t0 + chunk);
-                const char *kb = reinterpret_cast<const char *>(lw.kc + ((size_t)ag * d.max_seq + t0) * d.hd);
-                const char *vb = reinterpret_cast<const char *>(lw.vc + ((size_t)ag * d.max_seq + t0) * d.hd);
-                const uint32_t bytes = (t1 - t0) * d.hd * 4u;
-                for (uint32_t off = threadIdx.x * 128u; off < bytes; off += kThreads * 128u) { prefetch_l2(kb + off); prefetch_l2(vb + off); }
-            }
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-            // ---- P2: attention over (kv head, split) items ----
-            {
-                AttnArgs t{};
-                t.q = g.q; t.kraw = g.kraw; t.kc = lw.kc; t.vc = lw.vc; t.qnorm = lw.qnorm; t.knorm = lw.knorm;
-                t.rope_cos = g.rope_cos; t.rope_sin = g.rope_sin; t.xba = g.xba;
-                t.ws_m = g.ws_m; t.ws_l = g.ws_l; t.ws_acc = g.ws_acc; t.ticket = g.ticket; t.st = g.st;
-                t.nsplit_max = g.nsplit_max; t.chunk_cap = g.chunk_cap; t.d = d;
-                for (uint32_t item = cta; item < d.KV * nsplit; item += ncta) {
-                    attn_item<KVM, kThreads>(t, item / nsplit, item % nsplit, pos, range, chunk, nsplit, reinterpret_cast<float *>(dsm), attn_flag);
-                    __syncthreads();
-                }
-            }
-            pf(lw.w13_w, lw.w13_aux, 2 * d.F, d.E, lw.g_ffn);
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-            // ---- P3: quantise(xba) + O + residual ----
-            a.w = lw.wo_w; a.w_aux = lw.wo_aux; a.rows = d.E; a.n = d.q_dim;
-            a.src = g.xba; a.gain = nullptr; a.out = g.x; a.dump_codes = nullptr; a.dbg = dbg ? dbg + 16 : nullptr;
-            matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
-            NB_STAMP(dbg, 16 + 6);
-            pf(lw.w2_w, lw.w2_aux, d.E, d.F, nullptr);
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-            // ---- P4: rmsnorm + quantise + W1|W3 + SwiGLU ----
-            a.w = lw.w13_w; a.w_aux = lw.w13_aux; a.rows = 2 * d.F; a.n = d.E;
-            a.src = g.x; a.gain = lw.g_ffn; a.out = g.hb; a.dbg = dbg ? dbg + 32 : nullptr;
-            matvec_phase<QUANT, EPI_SWIGLU, RBL, LPG>(a, cta, ncta, dsm, ms);
-            NB_STAMP(dbg, 32 + 6);
-            if (l + 1 < d.L) pf(lws[l + 1].qkv_w, lws[l + 1].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[l + 1].g_attn);
-            else prefetch_row_blocks<QUANT, RBC>(g.cls_w, d.V, d.E, cta, ncta, 4, nullptr, 0, g.g_final);
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-            // ---- P5: quantise(hb) + W2 + residual ----
-            a.w = lw.w2_w; a.w_aux = lw.w2_aux; a.rows = d.E; a.n = d.F;
-            a.src = g.hb; a.gain = nullptr; a.out = g.x;
-            matvec_phase<QUANT, EPI_RESID, RBL, LPG>(a, cta, ncta, dsm, ms);
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-        }
-        // ---- classifier: final rmsnorm + quantise + matvec + penalty + per-CTA argmax ----
-        {
-            MatvecArgs a{};
-            a.d = d; a.st = g.st; a.st_rw = g.st; a.state_known = 1; a.pos_val = pos; a.pen_val = pen;
-            a.w = g.cls_w; a.w_aux = g.cls_aux; a.rows = d.V; a.n = d.E;
-            a.src = g.x; a.gain = g.g_final; a.out = g.logits;
-            a.seen = g.seen; a.seen_rw = g.seen; a.cls_val = g.cls_val; a.cls_idx = g.cls_idx; a.ids = g.ids;
-            matvec_phase<QUANT, EPI_CLS, RBC, LPG>(a, cta, ncta, dsm, ms);
-            pf(lws[0].qkv_w, lws[0].qkv_aux, d.q_dim + 2 * d.kv_dim, d.E, lws[0].g_attn);
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-            if (cta == 0) {
-                const uint32_t nxt = cls_finalize(a, ncta, ms);
-                if (step + 1 < g.n_steps) embed_row<kThreads>(g.emb_w, g.emb_aux, g.x, nxt, d);
-            }
-            grid_barrier(g.bar, target, ncta); NB_TRACE();
-        }
-    }
-#undef NB_TRACE
 }
 
 }  // namespace nb

@@ -18,7 +18,7 @@ u32p = C.POINTER(C.c_uint32)
 u8p = C.POINTER(C.c_uint8)
 i8p = C.POINTER(C.c_int8)
 
-FLAG_EXACT, FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_MEGA, FLAG_NO_CLUSTER = 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_EXACT, FLAG_NO_GRAPH, FLAG_NO_PDL, FLAG_NO_STREAM = 0x1, 0x2, 0x4, 0x10
 F_X, F_XBA, F_HB, F_Q, F_LOGITS, F_KROW, F_VROW, F_ACT_I8, F_ACT_SCALE = 0, 2, 4, 6, 9, 13, 14, 20, 21
 
 EXPORTS = [
@@ -136,8 +136,7 @@ class Engine:
         for n, _t in Config._fields_[:-1]:
             setattr(self, n, int(getattr(cfg, n)))
         self.vocab = self.vocab_size
-        self.path = {3: "cluster-resident kernel (16-CTA cluster, DSMEM activations, TMA weight ring)",
-                     2: "persistent megakernel (cooperative launch, L2 grid barriers)",
+        self.path = {4: "streaming kernel (persistent grid, per-CTA TMA ring over weights and KV, L2 grid barriers)",
                      1: "multi-kernel CUDA graph with PDL", 0: "multi-kernel direct launches"}[int(cfg.reserved[0])]
 
     # ---- LoRA plug-in ----
@@ -228,7 +227,7 @@ class Engine:
 
     def trace_token(self, token: int, pos: int) -> np.ndarray:
         """clock64() stamps (SM cycles) of CTA 0 after every grid barrier of one token (persistent kernel only)."""
-        cap = 1024 + 64
+        cap = 1024 + 256
         buf = np.zeros(cap, np.uint64); n = C.c_uint32(0)
         _check(lib().nb200_trace_token(self.h, token, pos, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(n)))
         return buf[: n.value]

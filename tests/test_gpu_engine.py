@@ -64,7 +64,7 @@ def reference_noise_floor(name, quant, gs, path, S):
     return floor
 
 
-@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_CLUSTER, E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA], ids=["cluster", "megakernel", "multikernel"])
+@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_STREAM], ids=["stream", "multikernel"])
 @pytest.mark.parametrize("name,quant,gs", TOY)
 def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags, monkeypatch):
     """Fast mode (parallel fp32 reductions): within the north-star tolerance, or -- where the reference's own
@@ -74,7 +74,6 @@ def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags, monkeypatc
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S = 40
-    monkeypatch.setenv("NB200_CLUSTER", "1"); monkeypatch.setenv("NB200_MEGA", "1")     # force each path where the model supports it
     eng = E.Engine(path, S, flags=path_flags); o = ob.NanoOracle(path, S)
     toks = mf.teacher_tokens(S, spec.vocab)
     floor = reference_noise_floor(name, quant, gs, path, S)
@@ -149,7 +148,6 @@ def test_layer_level_with_injected_inputs(name, quant, gs):
 def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty, monkeypatch):
     """generate_next_token semantics (prefill forcing, penalty over ids[0..pos), first-max argmax): ids identical
     to the oracle in exact mode; the device-resident loop reproduces the per-call API loop."""
-    monkeypatch.setenv("NB200_CLUSTER", "1"); monkeypatch.setenv("NB200_MEGA", "1")
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S, P = 40, 6
@@ -168,34 +166,24 @@ def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty, monkeyp
         eng.decode_greedy(ids2, P, S, penalty)
         assert ids2[:S].tolist() == ids_o[:S].tolist()
         eng.close()
-    # fast mode: device loop == API loop, and persistent megakernel == multi-kernel graph (same phase code)
+    # fast mode: device loop == API loop on both paths (multi-kernel graph, streaming kernel); the two paths use different
+    # (equally valid) reduction trees, so their ids must agree whenever every step's top-1/top-2 margin is above fast-mode noise
     runs = []
-    for flags in (E.FLAG_NO_CLUSTER, E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA):
+    for flags in (E.FLAG_NO_STREAM, 0):
         eng = E.Engine(path, S, flags=flags)
         a = np.zeros(S + 1, np.uint32); a[:P] = prompt
+        margins = []
         for pos in range(S - 1):
             a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
+            lg = np.sort(eng.logits()); margins.append(float(lg[-1] - lg[-2]))
         b = np.zeros(S + 1, np.uint32); b[:P] = prompt
         eng.decode_greedy(b, P, S, penalty)
-        assert a[:S].tolist() == b[:S].tolist()
-        runs.append((a[:S].tolist(), eng.logits()))
+        assert a[:S].tolist() == b[:S].tolist(), eng.path
+        runs.append((a[:S].tolist(), min(margins[P - 1:])))
         eng.close()
-    assert runs[0][0] == runs[1][0]
-    assert_bits_equal(runs[0][1], runs[1][1], "megakernel vs multi-kernel logits")
-    # cluster-resident kernel (default path when the model fits): API loop == device loop; ids equal to the other
-    # paths whenever every step's top-1/top-2 margin is comfortably above fast-mode noise
-    eng = E.Engine(path, S)
-    a = np.zeros(S + 1, np.uint32); a[:P] = prompt
-    margins = []
-    for pos in range(S - 1):
-        a[pos + 1] = eng.next_greedy(a, pos, 1 if pos < P - 1 else 0, penalty)
-        lg = np.sort(eng.logits()); margins.append(float(lg[-1] - lg[-2]))
-    b = np.zeros(S + 1, np.uint32); b[:P] = prompt
-    eng.decode_greedy(b, P, S, penalty)
-    assert a[:S].tolist() == b[:S].tolist()
-    if min(margins[P - 1:]) > 1e-3:
-        assert a[:S].tolist() == runs[0][0]
-    eng.close()
+    limit = max(TOL[quant], 1.5 * reference_noise_floor(name, quant, gs, path, S))
+    if min(runs[0][1], runs[1][1]) > 2 * limit:
+        assert runs[0][0] == runs[1][0]
     o.close()
 
 
@@ -234,7 +222,7 @@ def test_few_kv_heads_many_q_heads_shape():
     path = mf.cached_model(spec, mf.QUANT_F32, 128)
     S = 96
     toks = mf.teacher_tokens(S, spec.vocab)
-    for flags in (E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA, 0):
+    for flags in (E.FLAG_NO_STREAM, 0):
         eng = E.Engine(path, S, flags=flags); o = ob.NanoOracle(path, S)
         for pos in range(S):
             d = np.abs(eng.forward(toks[pos], pos) - o.forward(toks[pos], pos)).max()

@@ -60,7 +60,7 @@ def test_lora_matches_committed_reference_logits():
 
 def test_lora_enable_disable_and_unload_restore_the_base_model():
     path = mf.cached_model(SPEC, mf.QUANT_Q80, 64)
-    base = E.Engine(path, S, flags=E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA)
+    base = E.Engine(path, S, flags=E.FLAG_NO_STREAM)
     eng = E.Engine(path, S)
     path_before = eng.path
     toks = mf.teacher_tokens(S, SPEC.vocab)

@@ -13,7 +13,7 @@ from oracle import bindings as ob
 
 pytestmark = pytest.mark.gpu
 
-ONE_GPU = E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA        # the tensor-parallel kernels are the multi-kernel path's
+ONE_GPU = E.FLAG_NO_STREAM        # the tensor-parallel kernels are the multi-kernel path's
 
 
 def _need(n):

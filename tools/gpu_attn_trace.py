@@ -9,7 +9,7 @@ from nano_b200 import engine as E, modelfile as mf
 name = sys.argv[1] if len(sys.argv) > 1 else "qwen3-0.6b"
 seq = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 spec = mf.PRESETS[name]
-eng = E.Engine(mf.cached_model(spec, mf.QUANT_Q80, 128), seq, flags=E.FLAG_NO_CLUSTER | E.FLAG_NO_MEGA)
+eng = E.Engine(mf.cached_model(spec, mf.QUANT_Q80, 128), seq, flags=E.FLAG_NO_STREAM)
 print(eng.path)
 ids = np.zeros(seq + 1, np.uint32); ids[:16] = [17 + i % 10 for i in range(16)] if spec.arch == 0 else [1000 + i for i in range(16)]
 eng.decode_greedy(ids, 16, seq)

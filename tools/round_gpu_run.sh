@@ -11,8 +11,8 @@ b bench_q06_q80 --workload qwen3-0.6b-q80 --steps 2
 b bench_q06_q4k --workload qwen3-0.6b-q4k --steps 2 --no-cpu-baseline
 b bench_n168_f32 --workload nano-168m-f32 --no-cpu-baseline
 b bench_n168_q80_exact --exact --steps 2 --no-cpu-baseline
-b bench_n168_q80_multikernel --no-cluster --no-mega --steps 3 --no-cpu-baseline
-b bench_n168_q80_megakernel --no-cluster --steps 3 --no-cpu-baseline
+b bench_n168_q80_multikernel --no-stream --no-mega --steps 3 --no-cpu-baseline
+b bench_n168_q80_megakernel --no-stream --steps 3 --no-cpu-baseline
 b bench_q17_q80 --workload qwen3-1.7b-q80 --steps 1 --no-cpu-baseline
 b bench_q4b_q80 --workload qwen3-4b-q80 --steps 1 --no-cpu-baseline
 # launch lists of the default command (cluster path) and of the multi-kernel path; never a bench value
