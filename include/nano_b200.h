@@ -19,9 +19,10 @@
  *                            repetition penalty :1156-1167 + sample_argmax :1026-1037)
  *   nb200_decode_greedy   <- the llm_session_step loop of infer/infer.c:1243-1310 with the token fed back
  *                            on the device (no host round trip per token)
- *   nb200_op_*            <- rmsnorm :601, softmax :616, matmul :637, matmul_quant :654, rope :681,
- *                            rope_qwen3 :692 (infer/infer.c); quantize tensor.c:21,
- *                            quantize_tensor_q4k_in_situ tensor.c:281, matmul_q4k tensor.c:438
+ *   nb200_op_*            <- rmsnorm :601, matmul :637, matmul_quant :654 (infer/infer.c); quantize tensor.c:21,
+ *                            quantize_tensor_q4k_in_situ tensor.c:281, matmul_q4k tensor.c:438.  (softmax :616, rope :681 and
+ *                            rope_qwen3 :692 have no stand-alone entry point: they exist only fused inside the attention kernels
+ *                            and are pinned through the exact-mode K-row / logits tests.)
  */
 #ifndef NANO_B200_H
 #define NANO_B200_H

@@ -6,7 +6,7 @@
  * reference's OWN headers and only LINKED against our library, so what must match is the ABI: struct layouts
  * (callers read ctx->llm->config.*, llm->arch/quant_type/group_size, ctx->tokenizer->vocab[], write
  * ctx->sampler->temperature/top_p and ctx->observation*: SURVEY finding 8) and the exported prototypes
- * (infer.h:253-282).  tests/test_abi_layout.py checks every size/offset below against the reference's
+ * (infer.h:253-282).  tests/test_boundary.py checks every size/offset below against the reference's
  * headers (through oracle/ref_harness.c:orh_abi_layout) whenever /root/reference is available, and against
  * the committed tests/golden/abi_layout.json otherwise.
  *

@@ -515,8 +515,8 @@ int setup_stream(nb200_engine *e) {
     // ring stage: at least two row units of the longest row, 16 KB by default
     uint32_t stage_bytes = env_u32("NB200_STAGE_KB", 16) * 1024u;
     if (stage_bytes < 2 * unit_b_max + 16u) stage_bytes = (2 * unit_b_max + 16u + 1023u) & ~1023u;
-    uint32_t kv_rows = (stage_bytes / (2u * d.hd * 4u)) & ~7u;
-    if (kv_rows < 8) return 0;
+    uint32_t kv_rows = (stage_bytes / (2u * d.hd * 4u)) & ~3u;
+    if (kv_rows < 4) return 0;
     uint64_t off = 0;
     uint32_t ntl[5];
     for (int i = 0; i < 5; i++) {
@@ -527,6 +527,14 @@ int setup_stream(nb200_engine *e) {
         T -= T % sk.unit_rows;
         if (T > max_rows) T = max_rows;
         if (T < sk.unit_rows) return 0;
+        // many rows per CTA: throughput mode, every tile is consumed by one warp -- small tiles so that all 15 warps have one
+        sk.owned = (max_rows >= env_u32("NB200_OWNED_ROWS", 32) || (uint64_t)max_rows * rowb >= (uint64_t)env_u32("NB200_OWNED_KB", 32) * 1024u) ? 1u : 0u;
+        if (sk.owned) {
+            uint32_t t2 = (max_rows + kConsWarps - 1) / kConsWarps;
+            t2 = ((t2 + sk.unit_rows - 1) / sk.unit_rows) * sk.unit_rows;
+            if (t2 < 2u) t2 = 2u;
+            if (t2 < T) T = t2;
+        }
         sk.tile_rows = T;
         sk.tile_stride = (T * rowb + 15u) & ~15u;
         ntl[i] = (max_rows + T - 1) / T;
@@ -556,7 +564,7 @@ int setup_stream(nb200_engine *e) {
     const uint32_t nst_cap = env_u32("NB200_STAGES", kStMaxStages);
     if (nst > nst_cap) nst = nst_cap;
     if (nst > (uint32_t)kStMaxStages) nst = kStMaxStages;
-    if (nst < 2u * (uint32_t)kStSegTiles) return 0;      // an attention segment keeps kStSegTiles tiles resident while the next ones arrive
+    if (nst < (uint32_t)kStSegTiles + 4u) return 0;      // an attention segment keeps kStSegTiles tiles resident while the next ones arrive
     const uint32_t smem = region0 + nst * stage_bytes;
     cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
@@ -589,6 +597,7 @@ int setup_stream(nb200_engine *e) {
     CK(cudaHostGetDevicePointer((void **)&e->st_err_dev, e->st_err_host, 0));
 
     g.stream = stream; g.nstages = nst; g.stage_bytes = stage_bytes; g.kv_tile_rows = kv_rows;
+    g.kv_tile_magic = (uint32_t)((0x100000000ull + kv_rows - 1) / kv_rows);
     g.g_attn = e->norm_attn; g.g_ffn = e->norm_ffn; g.g_final = e->norm_final;
     g.qnorm = e->qnorm; g.knorm = e->knorm; g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
     g.emb_w = e->emb.w; g.emb_aux = e->emb.aux;
@@ -606,7 +615,7 @@ int setup_stream(nb200_engine *e) {
     g.cls_val = e->cls_val; g.cls_idx = e->cls_idx;
     g.st = e->st; g.ids = e->ids_dev; g.seen = e->seen; g.bar = e->bar; g.err = e->st_err_dev;
     g.n_steps = 1; g.nsplit_max = nsplit_max;
-    uint32_t ct = 65536u / (d.hd * 8u); ct &= ~7u; if (ct < 32) ct = 32;
+    uint32_t ct = 32768u / (d.hd * 8u); ct &= ~7u; if (ct < 32) ct = 32;      // measured: ~32 KB of K+V per (kv head, split) item
     g.chunk_target = env_u32("NB200_ATTN_CHUNK", ct);
     if (g.chunk_target < 8) g.chunk_target = 8;
     g.d = d;
@@ -699,6 +708,8 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
         if (d.exact) return fail(NB200_EINVAL, "tensor parallel runs in fast mode only");
         if (d.KV % T || d.E % (2 * T) || d.F % T || d.V % T) return fail(NB200_EINVAL, "tensor parallel size %u does not divide kv heads / n_embd / n_hidden / vocab", T);
         if (d.hd > 128 || (d.arch == 3u && (d.hd & (d.hd - 1)) != 0)) return fail(NB200_EINVAL, "tensor parallel needs head_dim <= 128 (power of two for Qwen3)");
+        const uint32_t kvm = d.H / d.KV;      // only these ratios have a tensor-parallel attention kernel (run_layer)
+        if (kvm != 1 && kvm != 2 && kvm != 4 && kvm != 8) return fail(NB200_EINVAL, "tensor parallel needs n_head / n_kv_head in {1, 2, 4, 8} (got %u)", kvm);
     }
 
     // ---- parameter map (infer.c:100-217) ----
@@ -706,7 +717,7 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     const uint8_t *cur = img + 256 + tok_bytes;
     const uint8_t *end = img + image_bytes;
     const uint64_t L = d.L, E = d.E, V = d.V, F = d.F, QD = d.q_dim, KD = d.kv_dim;
-    auto need = [&](uint64_t bytes) { return (uint64_t)(end - cur) >= bytes; };
+    auto need = [&](uint64_t bytes) { return cur <= end && (uint64_t)(end - cur) >= bytes; };
     if (cur > end || !need((2 * L + 1) * E * 4)) return fail(NB200_EINVAL, "file truncated (norms)");
     DM(e->norm_attn, L * E * 4); DM(e->norm_ffn, L * E * 4); DM(e->norm_final, E * 4);
     CK(cudaMemcpy(e->norm_attn, cur, L * E * 4, cudaMemcpyHostToDevice)); cur += L * E * 4;
@@ -755,7 +766,10 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
             for (uint64_t l = 0; l < L; l++) { src_w[t].push_back(blocks + l * per_layer * 160); src_a[t].push_back(nullptr); }
         }
     }
-    if (d.arch == 2u) cur += L * (QD + 2 * KD) * 4;     // Qwen2 biases: parsed, never applied (infer.c:175-179, 788-790)
+    if (d.arch == 2u) {                                 // Qwen2 biases: parsed, never applied (infer.c:175-179, 788-790)
+        if (!need(L * (QD + 2 * KD) * 4)) return fail(NB200_EINVAL, "file truncated (Qwen2 biases)");
+        cur += L * (QD + 2 * KD) * 4;
+    }
     if (d.arch == 3u) {
         if (!need(2 * L * d.hd * 4)) return fail(NB200_EINVAL, "file truncated (q/k norm)");
         DM(e->qnorm, L * d.hd * 4); DM(e->knorm, L * d.hd * 4);
@@ -774,7 +788,12 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
                 for (uint32_t i = 0; i < half; i++) { c[(size_t)p * half + i] = cosf(p * fr[i]); s[(size_t)p * half + i] = sinf(p * fr[i]); }
             CK(cudaMemcpy(e->rope_cos, c.data(), tb, cudaMemcpyHostToDevice));
             CK(cudaMemcpy(e->rope_sin, s.data(), tb, cudaMemcpyHostToDevice));
-            cur += 2 * (size_t)d.block_size * half * 4;      // the reference skips a table it does not read
+            // the reference steps over a table it never reads (infer.c:201-202); files of tied models may simply end here
+            // (Q4K files of arch 3 always do, tools/export_q4k.c:176-204) -- only an untied classifier needs the gap to exist
+            const uint64_t gap = 2 * (uint64_t)d.block_size * half * 4;
+            if (need(gap)) cur += gap;
+            else if (!tied && d.quant == 0x80u) return fail(NB200_EINVAL, "file truncated (RoPE gap before the classifier)");
+            else cur = end;
         } else {
             const size_t full = (size_t)d.block_size * half * 4;
             if (!need(2 * full)) return fail(NB200_EINVAL, "file truncated (RoPE table)");
@@ -784,6 +803,8 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
         }
     }
     const uint8_t *cls_w = nullptr, *cls_a = nullptr;
+    if (d.quant == 0x00u && !tied)      // the reference points an untied F32 classifier at the start of the parameter block (infer.c:215): refuse, do not copy the bug
+        return fail(NB200_EINVAL, "untied F32 classifier is not supported (the reference's own pointer for it is wrong, infer.c:215)");
     if (d.quant == 0x80u && !tied) {
         if (cur > end || !need(V * E + V * E / d.gs * 4)) return fail(NB200_EINVAL, "file truncated (classifier)");
         cls_w = cur; cls_a = cur + V * E;
@@ -888,9 +909,13 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     CK(cudaDeviceSynchronize());
 
     {
-        // Default path in fast mode on one GPU: the grid-wide streaming kernel.  NB200_STREAM=0 / NB200_FLAG_NO_STREAM forbid it.
+        // Default path in fast mode on one GPU, by measured speed (profiles/r2_paths.md): the streaming kernel for F32 / Q4K models and for
+        // Q80 models under 256 MB of weights (latency-bound: one launch, no per-phase kernel boundary); the CUDA-graph multi-kernel path
+        // for larger Q80 models.  NB200_STREAM=1 forces the streaming kernel where the shape allows it, NB200_STREAM=0 / NB200_FLAG_NO_STREAM forbid it.
         const char *st_env = getenv("NB200_STREAM");
-        if (T == 1 && !(flags & NB200_FLAG_NO_STREAM) && !(st_env && atoi(st_env) == 0)) { if ((r = setup_stream(e))) return r; }
+        const bool st_forced = st_env && atoi(st_env) == 1, st_off = (st_env && atoi(st_env) == 0) || (flags & NB200_FLAG_NO_STREAM);
+        const bool st_default = d.quant != 0x80u || e->weight_bytes < (256ull << 20);
+        if (T == 1 && !st_off && (st_default || st_forced)) { if ((r = setup_stream(e))) return r; }
     }
     e->path_stream = e->use_stream;
     if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
@@ -979,7 +1004,13 @@ int nb200_lora_unload(nb200_engine *e) {
     if (!e) return fail(NB200_EINVAL, "null engine");
     if (!e->lora.loaded) return 0;
     int r = lora_set_active(e, false);
-    for (int m = 0; m < 4; m++) { e->lora.a[m] = nullptr; e->lora.b[m] = nullptr; }      // device memory is released with the engine
+    auto drop = [&](float *&p) {
+        if (!p) return;
+        for (auto it = e->allocs.begin(); it != e->allocs.end(); ++it) if (*it == (void *)p) { e->allocs.erase(it); break; }
+        cudaFree(p); p = nullptr;
+    };
+    for (int m = 0; m < 4; m++) { drop(e->lora.a[m]); drop(e->lora.b[m]); }
+    drop(e->lora.t); drop(e->lora.o1);
     e->lora.loaded = false; e->lora.rank = 0;
     return r;
 }
@@ -1127,7 +1158,8 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     for (uint32_t i = 0; i < n_prompt; i++) if (ids[i] >= e->d.V) return fail(NB200_EINVAL, "id out of range");
     CK(cudaSetDevice(e->device));
     int r;
-    cudaEvent_t ev[3];
+    struct Events { cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; ~Events() { for (auto v : ev) if (v) cudaEventDestroy(v); } } evs;     // destroyed on every return path
+    cudaEvent_t (&ev)[3] = evs.ev;
     for (auto &v : ev) CK(cudaEventCreate(&v));
     if ((r = push_state(e, 0, 1, n_prompt, 1, penalty, 0, 0))) return r;
     CK(cudaMemcpyAsync(e->ids_dev, ids, (size_t)n_prompt * 4, cudaMemcpyHostToDevice, e->stream));
@@ -1147,7 +1179,6 @@ int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint3
     CK(cudaEventElapsedTime(&b, ev[1], ev[2]));
     if (prefill_ms) *prefill_ms = a;
     if (device_ms) *device_ms = b;
-    for (auto &v : ev) cudaEventDestroy(v);
     return tp_check(e);
 }
 

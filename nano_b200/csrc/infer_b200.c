@@ -162,6 +162,8 @@ static LoRA *lora_from_image(LLM *llm, uint8_t *buffer, uint64_t bytes) {
     p->params.wo_lora_a = f; f += L * r * E;  p->params.wo_lora_b = f;
     return p;
 }
+/* file buffers that load_lora() allocated itself (the LoRA struct is ABI-fixed and has no room for an ownership flag) */
+static struct { LoRA *lora; void *buf; } g_lora_owned[8];
 LoRA *load_lora_from_buffer(LLM *llm, uint8_t *buffer) { return lora_from_image(llm, buffer, 0); }
 LoRA *load_lora(LLM *llm, char *lora_path) {
     FILE *fp = fopen(lora_path, "rb");
@@ -173,11 +175,14 @@ LoRA *load_lora(LLM *llm, char *lora_path) {
     if (!buf) die("load_lora: allocation failed");
     if (fread(buf, 1, n, fp) != n) { fclose(fp); exit(EXIT_FAILURE); }
     fclose(fp);
-    return lora_from_image(llm, buf, n);
+    LoRA *p = lora_from_image(llm, buf, n);
+    for (int i = 0; i < 8; i++) if (!g_lora_owned[i].lora) { g_lora_owned[i].lora = p; g_lora_owned[i].buf = buf; break; }
+    return p;
 }
 /* infer.c:521-534 frees interior pointers of a single allocation (undefined behaviour); here: drop the device copy and the struct */
 void free_lora(LLM *llm, LoRA *lora) {
     if (llm) nb200_lora_unload(engine_of(llm));
+    for (int i = 0; i < 8; i++) if (lora && g_lora_owned[i].lora == lora) { free(g_lora_owned[i].buf); g_lora_owned[i].lora = NULL; g_lora_owned[i].buf = NULL; }
     free(lora);
 }
 
@@ -383,6 +388,7 @@ void seq2seq(Nano_Context *ctx, wchar_t *input_list, wchar_t *output_list, uint3
     LLM *llm = ctx->llm;
     nb200_engine *e = engine_of(llm);
     const uint32_t V = llm->config.vocab_size;
+    if (nb200_lora_enable(e, 0) != NB200_OK) die("seq2seq (use_lora)");       /* the reference passes lora = NULL for the whole of seq2seq (infer.c:1365-1402) */
     for (uint32_t sweep = 0; sweep < llm->config.n_layer; sweep++)
         for (uint32_t pos = 0; pos < max_seq_len; pos++) {
             notify_forward(ctx);

@@ -130,20 +130,36 @@ __device__ __forceinline__ void st_attn_plan(uint32_t range, uint32_t nsplit_max
 
 struct StRing {
     uint64_t *full, *empty;
+    volatile uint32_t *tile_id;   // [nstages] running index of the tile that owns the stage (written by the producer before the copy).
+                                  // Warp-owned tiles are consumed out of step, and mbarrier parity is only unambiguous one phase
+                                  // apart: a consumer first waits for ITS tile to own the stage, then for the bytes.
     unsigned char *buf;
     uint32_t nstages, stage_bytes;
 };
+__device__ __forceinline__ void mbar_arrive_n(uint64_t *bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 struct StCursor { uint32_t s, par; };     // stage and parity of the next tile (producer: empty parity; consumer: full parity)
 __device__ __forceinline__ void st_advance(StCursor &c, uint32_t nstages) { if (++c.s == nstages) { c.s = 0; c.par ^= 1u; } }
 struct StOwn { uint32_t row0[5], rows[5]; };      // the rows this CTA owns of every phase kind (shared memory; computed once)
+// How the 32 lanes of a warp share the rows of a tile, per phase kind (computed once per launch, kept in shared memory:
+// run-time integer divisions cost ~150 cycles each and sat on every phase's critical path).
+// Q80: a row of G groups is owned by a team of gteam * lg2 lanes (lg2 lanes split the 16-byte chunks of one group);
+// rw = rows per warp pass.  F32 / Q4K: one warp per row.
+struct StGeo {
+    uint8_t lg2[5], gteam[5], ts[5], rw[5], mode[5];      // mode: 0 single rows, 1 pair (w1, w3) on adjacent teams, 2 pair done by one team
+    uint8_t team[5][32], tl[5][32];                       // per lane: team index within the warp, lane index within the team
+    uint8_t gl[5][32], ul[5][32];                         // per lane: group within the team pass, lane within the group
+};
 
 // ---------------------------------------------------------------- producer (warp 15, lane 0)
-__device__ __forceinline__ void st_issue_kind(const StreamArgs &g, const StRing &r, StCursor &c, const StKind &k, const uint8_t *base, uint32_t rows) {
+__device__ __forceinline__ void st_issue_kind(const StreamArgs &g, const StRing &r, StCursor &c, uint32_t &issued, const StKind &k, const uint8_t *base, uint32_t rows) {
     const uint8_t *src = base + k.off;
     for (uint32_t done = 0; done < rows; done += k.tile_rows) {
         const uint32_t tr = min(k.tile_rows, rows - done);
         const uint32_t bytes = (tr * (k.row_stride + k.aux_stride) + 15u) & ~15u;
         mbar_wait(&r.empty[c.s], c.par, g.err, 0x10u);
+        r.tile_id[c.s] = issued++;
         mbar_expect_tx(&r.full[c.s], bytes);
         bulk_g2s(r.buf + (size_t)c.s * r.stage_bytes, src, bytes, &r.full[c.s]);
         st_advance(c, r.nstages);
@@ -155,6 +171,7 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
                                    uint32_t pos0, uint32_t causal, uint32_t advance) {
     const Dims &d = g.d;
     StCursor c{0u, 1u};                       // parity 1 passes at once on a stage's first use
+    uint32_t issued = 0;                      // running tile index
     const uint8_t *base = g.stream + (uint64_t)cta * g.cta_stride;
     const size_t kvl = (size_t)d.KV * d.max_seq * d.hd;
     for (uint32_t step = 0; step < g.n_steps; step++) {
@@ -164,7 +181,7 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
         st_attn_plan(range, g.nsplit_max, g.chunk_target, nsplit, chunk);
         for (uint32_t l = 0; l < d.L; l++) {
             const uint8_t *lb = base + (uint64_t)l * g.layer_stride;
-            st_issue_kind(g, r, c, g.kind[SK_QKV], lb, own.rows[SK_QKV]);
+            st_issue_kind(g, r, c, issued, g.kind[SK_QKV], lb, own.rows[SK_QKV]);
             if (cta < d.KV * nsplit) {
                 const uint32_t kvh = cta / nsplit, sp = cta % nsplit;
                 const uint32_t t0 = min(range, sp * chunk), t1 = min(range, t0 + chunk);
@@ -179,6 +196,7 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
                         while (*progress < step) { if (clock64() - c0 > 4000000000ll) st_give_up(g.err, 0x11u); }
                     }
                     mbar_wait(&r.empty[c.s], c.par, g.err, 0x12u);
+                    r.tile_id[c.s] = issued++;
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     mbar_expect_tx(&r.full[c.s], 2u * bytes);
                     unsigned char *dst = r.buf + (size_t)c.s * r.stage_bytes;
@@ -187,11 +205,11 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
                     st_advance(c, r.nstages);
                 }
             }
-            st_issue_kind(g, r, c, g.kind[SK_O], lb, own.rows[SK_O]);
-            st_issue_kind(g, r, c, g.kind[SK_W13], lb, own.rows[SK_W13]);
-            st_issue_kind(g, r, c, g.kind[SK_W2], lb, own.rows[SK_W2]);
+            st_issue_kind(g, r, c, issued, g.kind[SK_O], lb, own.rows[SK_O]);
+            st_issue_kind(g, r, c, issued, g.kind[SK_W13], lb, own.rows[SK_W13]);
+            st_issue_kind(g, r, c, issued, g.kind[SK_W2], lb, own.rows[SK_W2]);
         }
-        st_issue_kind(g, r, c, g.kind[SK_CLS], base + g.cls_off, own.rows[SK_CLS]);
+        st_issue_kind(g, r, c, issued, g.kind[SK_CLS], base + g.cls_off, own.rows[SK_CLS]);
     }
 }
 
@@ -268,41 +286,49 @@ __device__ __forceinline__ void st_prep(const StreamArgs &g, const unsigned long
             }
         }
     } else {
-        constexpr uint32_t gs = (QUANT == 0x80) ? LPG * 16u : 128u;      // F32: 128-element slots, no grouping semantics
-        constexpr uint32_t LG = gs / 4u;                                 // lanes per group (16 or 32)
+        // Q80: a group (gs elements) is held by LG = gs/8 lanes, 8 elements (two float4) per lane, GW = 32/LG groups per warp slot.
+        // F32: no grouping semantics, 256-element slots.
+        constexpr uint32_t gs = (QUANT == 0x80) ? LPG * 16u : 256u;
+        constexpr uint32_t LG = gs / 8u;                                 // lanes per group (8, 16 or 32)
         constexpr uint32_t GW = 32u / LG;                                // groups per warp slot
-        static_assert(LG == 16 || LG == 32, "stream kernel: Q80 group size 64 or 128");
+        static_assert(LG == 8 || LG == 16 || LG == 32, "stream kernel: Q80 group size 64 or 128");
         const uint32_t G = (n + gs - 1u) / gs;                           // F32: n % 4 == 0 only, the last slot may be partial
         const uint32_t sub = lane / LG, li = lane % LG;
-        float4 v[kStKmax];
+        float4 v[kStKmax][2];
         if (ssrc) {
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
-                v[j] = (i < n) ? *reinterpret_cast<const float4 *>(ssrc + i) : make_float4(0, 0, 0, 0);
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) v[j][h] = (i + 4u * h < n) ? *reinterpret_cast<const float4 *>(ssrc + i + 4 * h) : make_float4(0, 0, 0, 0);
             }
         } else {
             // every load of the thread is in flight before the first epoch is looked at
-            unsigned long long w[kStKmax][4];
+            unsigned long long w[kStKmax][8];
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
-                if (i < n) { xw_ld2(xsrc + i, w[j][0], w[j][1]); xw_ld2(xsrc + i + 2, w[j][2], w[j][3]); }
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
+#pragma unroll
+                for (int h = 0; h < 4; h++) if (i + 2u * h < n) xw_ld2(xsrc + i + 2 * h, w[j][2 * h], w[j][2 * h + 1]);
             }
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
-                v[j] = make_float4(0, 0, 0, 0);
-                if (i < n) {
-                    if (xw_ok(w[j][0], need) && xw_ok(w[j][1], need) && xw_ok(w[j][2], need) && xw_ok(w[j][3], need))
-                        v[j] = make_float4(xw_val(w[j][0]), xw_val(w[j][1]), xw_val(w[j][2]), xw_val(w[j][3]));
-                    else v[j] = xw_poll4_slow(xsrc + i, need, g.err);
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    v[j][h] = make_float4(0, 0, 0, 0);
+                    if (i + 4u * h < n) {
+                        const unsigned long long *ww = w[j] + 4 * h;
+                        if (xw_ok(ww[0], need) && xw_ok(ww[1], need) && xw_ok(ww[2], need) && xw_ok(ww[3], need))
+                            v[j][h] = make_float4(xw_val(ww[0]), xw_val(ww[1]), xw_val(ww[2]), xw_val(ww[3]));
+                        else v[j][h] = xw_poll4_slow(xsrc + i + 4 * h, need, g.err);
+                    }
                 }
             }
         }
         float ss = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kStKmax; j++) ss = sq(v[j], ss);
+        for (int j = 0; j < kStKmax; j++) { ss = sq(v[j][0], ss); ss = sq(v[j][1], ss); }
         ST_DBG(1);
         float inv = 1.0f;
         if (gain) inv = inverse(ss);
@@ -311,40 +337,44 @@ __device__ __forceinline__ void st_prep(const StreamArgs &g, const unsigned long
         for (int j = 0; j < kStKmax; j++) {
             const uint32_t g0 = (warp + kConsWarps * j) * GW;
             if (g0 < G) {                                            // warp-uniform
-                const uint32_t gi = g0 + sub, i = gi * gs + li * 4u;
-                const bool on = i < n;
-                float4 a = v[j];
-                if (gain && on) a = nrm(a, __ldg(reinterpret_cast<const float4 *>(gain + i)), inv);
+                const uint32_t gi = g0 + sub, i = gi * gs + li * 8u;
+                float4 a0 = v[j][0], a1 = v[j][1];
+                const bool on0 = i < n, on1 = i + 4u < n;
+                if (gain) {
+                    if (on0) a0 = nrm(a0, __ldg(reinterpret_cast<const float4 *>(gain + i)), inv);
+                    if (on1) a1 = nrm(a1, __ldg(reinterpret_cast<const float4 *>(gain + i + 4)), inv);
+                }
                 if constexpr (QUANT == 0x00) {
-                    if (on) *reinterpret_cast<float4 *>(act + (size_t)i * 4u) = a;
+                    if (on0) *reinterpret_cast<float4 *>(act + (size_t)i * 4u) = a0;
+                    if (on1) *reinterpret_cast<float4 *>(act + (size_t)i * 4u + 16u) = a1;
                 } else {
                     int8_t *codes = reinterpret_cast<int8_t *>(act);
                     float *scales = reinterpret_cast<float *>(act + ((n + 15u) & ~15u));
                     // tensor.c:21-46.  amax over the group with one REDUX (the values are non-negative: uint order == float order);
                     // the exact scale amax/127 is off the codes' critical path; codes come from q = v * (127/amax) rounded with the
                     // magic-number add, and any q within 1e-3 of a .5 boundary goes through the exact division + round().
-                    float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
-                    const uint32_t gmask = (LG == 32u) ? 0xffffffffu : (0xffffu << (16u * sub));
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    float amax = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) amax = fmaxf(amax, fabsf(av[u]));
+                    const uint32_t gmask = (LG == 32u) ? 0xffffffffu : (((1u << LG) - 1u) << (LG * sub));
                     amax = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(amax)));
                     const float sc = __fdiv_rn(amax, 127.0f);
                     const float rinv = __fdividef(127.0f, amax);
-                    if (on) {
-                        uint32_t pk = 0;
+                    if (on0) {
+                        uint32_t pk[2] = {0u, 0u};
                         if (sc != 0.0f) {
-                            const float av[4] = {a.x, a.y, a.z, a.w};
-                            int cq[4];
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
+                            for (int u = 0; u < 8; u++) {
                                 const float q = av[u] * rinv, aq = fabsf(q);
                                 const float rr = aq + 12582912.0f;                 // 1.5 * 2^23: the integer nearest to aq sits in the mantissa
                                 const float cf = rr - 12582912.0f;
                                 int c = __float_as_int(rr) - 0x4b400000;
                                 if (fabsf(aq - cf) > 0.499f) c = abs(q80_code_slow(av[u], sc));       // rare: within 1e-3 of a tie
-                                cq[u] = q < 0.0f ? -c : c;
+                                pk[u >> 2] |= ((uint32_t)(q < 0.0f ? -c : c) & 0xffu) << (8 * (u & 3));
                             }
-                            pk = ((uint32_t)cq[0] & 0xffu) | (((uint32_t)cq[1] & 0xffu) << 8) | (((uint32_t)cq[2] & 0xffu) << 16) | (((uint32_t)cq[3] & 0xffu) << 24);
                         }
-                        *reinterpret_cast<uint32_t *>(codes + i) = pk;
+                        *reinterpret_cast<uint2 *>(codes + i) = make_uint2(pk[0], pk[1]);
                         if (li == 0) scales[gi] = sc;
                     }
                 }
@@ -357,35 +387,84 @@ __device__ __forceinline__ void st_prep(const StreamArgs &g, const unsigned long
 }
 
 // ---------------------------------------------------------------- row dots on a shared-memory tile
-// Q80, matmul_quant infer.c:654-679: one LANE per quantisation group.  A row of G = n/gs groups is owned by a team of
-// LPR = min(G, 32) lanes (32/LPR rows per warp pass; rows longer than 32 groups take several passes).  A lane walks the
-// 16-byte chunks of its group in an order rotated by its group index, so the lanes of a quarter-warp hit different banks;
-// the integer group sum needs no cross-lane traffic at all.  The fp32 terms are then summed in group order (the reference's
-// left-to-right sum) by every lane of the team through G shuffles, which leaves the row value in all of the team's lanes.
+// Q80, matmul_quant infer.c:654-679.  A row of G = n/gs groups is owned by a team of gteam * LG2 lanes: LG2 lanes share
+// the 16-byte chunks of one group (chunk order rotated by the group index: the lanes of a quarter-warp hit different
+// banks), an xor-shuffle over those LG2 lanes leaves the exact integer group sum in each of them, and the fp32 terms are
+// summed in group order (the reference's left-to-right sum) by every lane of the team, so the row value ends up in all of
+// the team's lanes.  Rows longer than gteam groups take several passes (LG2 = 1 then).
 template <int LPG>
 __device__ __forceinline__ float st_row_q80_lpg(const unsigned char *wrow, const float *srow, uint32_t n, const unsigned char *act,
-                                                uint32_t lpr, uint32_t tl, uint32_t team_base) {
+                                                uint32_t lg2, uint32_t gteam, uint32_t gl, uint32_t u, uint32_t team_base, unsigned long long *dbg = nullptr) {
     constexpr uint32_t gs = LPG * 16;
+    ST_DBG(10);
     const float *xs = reinterpret_cast<const float *>(act + ((n + 15u) & ~15u));
     const uint32_t G = n / gs;
     float val = 0.0f;
-    for (uint32_t g0 = 0; g0 < G; g0 += 32u) {                 // warp-uniform
-        const uint32_t gi = g0 + tl;
-        const bool on = gi < G;
-        const uint32_t gc = on ? gi : G - 1u;
+    for (uint32_t g0 = 0; g0 < G; g0 += gteam) {               // warp-uniform
+        const uint32_t gi = g0 + gl;
+        const uint32_t gc = gi < G ? gi : G - 1u;
         const unsigned char *wp = wrow + (size_t)gc * gs, *xp = act + (size_t)gc * gs;
         int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-        for (int c = 0; c < LPG; c++) {
-            const uint32_t off = ((uint32_t)(c + tl) % LPG) * 16u;
+        for (uint32_t c = u; c < (uint32_t)LPG; c += lg2) {
+            const uint32_t off = ((c + gl * lg2) % LPG) * 16u;
             const int4 w = *reinterpret_cast<const int4 *>(wp + off), xq = *reinterpret_cast<const int4 *>(xp + off);
             a0 = __dp4a(w.x, xq.x, a0); a1 = __dp4a(w.y, xq.y, a1); a2 = __dp4a(w.z, xq.z, a2); a3 = __dp4a(w.w, xq.w, a3);
         }
-        const float term = __fmul_rn(__fmul_rn((float)((a0 + a1) + (a2 + a3)), srow[gc]), xs[gc]);
-        const uint32_t cnt = min(lpr, G - g0);
-        for (uint32_t j = 0; j < cnt; j++) val = __fadd_rn(val, __shfl_sync(0xffffffffu, term, team_base + j));      // cnt is warp-uniform
+        int isum = (a0 + a1) + (a2 + a3);
+        for (uint32_t o = 1; o < lg2; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+        ST_DBG(11);
+        const float term = __fmul_rn(__fmul_rn((float)isum, srow[gc]), xs[gc]);
+        ST_DBG(12);
+        const uint32_t cnt = min(gteam, G - g0);
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 8u) {           // the shuffles of a batch are issued before the ordered adds
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) t8[j] = __shfl_sync(0xffffffffu, term, team_base + ((j0 + j) * lg2 & 31u));
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (j0 + j < cnt) val = __fadd_rn(val, t8[j]);
+        }
+        ST_DBG(13);
     }
     return val;
+}
+// Throughput form for warp-owned tiles: a whole warp owns RB rows, lanes split K in 16-byte chunks (512 bytes per step,
+// conflict-free), integer group sums via xor-shuffles inside the LPG lanes of a group, ordered fp32 combine via shuffles;
+// the row values end up in every lane.
+template <int LPG, int RB>
+__device__ __forceinline__ void st_rows_q80_warp(const unsigned char *wrow, uint32_t row_stride, const unsigned char *srow, uint32_t aux_stride,
+                                                 uint32_t n, const unsigned char *act, float (&val)[RB]) {
+    constexpr uint32_t gs = LPG * 16;
+    constexpr int GPS = 32 / LPG;
+    const int lane = threadIdx.x & 31;
+    const float *xs = reinterpret_cast<const float *>(act + ((n + 15u) & ~15u));
+#pragma unroll
+    for (int r2 = 0; r2 < RB; r2++) val[r2] = 0.0f;
+    for (uint32_t k0 = 0; k0 < n; k0 += 512u) {
+        const uint32_t k = k0 + lane * 16u;
+        const bool on = k < n;
+        const uint32_t kc = on ? k : 0u;
+        const int4 xq = on ? *reinterpret_cast<const int4 *>(act + kc) : make_int4(0, 0, 0, 0);
+        const float xsc = xs[kc / gs];
+        float term[RB];
+#pragma unroll
+        for (int r2 = 0; r2 < RB; r2++) {
+            const int4 w = *reinterpret_cast<const int4 *>(wrow + (size_t)r2 * row_stride + kc);
+            const float ws = reinterpret_cast<const float *>(srow + (size_t)r2 * aux_stride)[kc / gs];
+            int isum = __dp4a(w.x, xq.x, 0);
+            isum = __dp4a(w.y, xq.y, isum); isum = __dp4a(w.z, xq.z, isum); isum = __dp4a(w.w, xq.w, isum);
+#pragma unroll
+            for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+            term[r2] = __fmul_rn(__fmul_rn((float)isum, ws), xsc);
+        }
+#pragma unroll
+        for (int gq = 0; gq < GPS; gq++) {
+#pragma unroll
+            for (int r2 = 0; r2 < RB; r2++) {
+                const float t = __shfl_sync(0xffffffffu, term[r2], gq * LPG);
+                if (k0 + gq * gs < n) val[r2] = __fadd_rn(val[r2], t);
+            }
+        }
+    }
 }
 // F32: matmul infer.c:637-651, fast mode (one warp per row: lane-split FMA + tree)
 __device__ __forceinline__ float st_row_f32(const unsigned char *wrow, uint32_t n, const unsigned char *act) {
@@ -449,82 +528,131 @@ __device__ __forceinline__ float st_row_q4k(const unsigned char *wrow, const uns
 }
 
 // ---------------------------------------------------------------- one matvec phase: tiles from the ring -> epilogue
-// The epilogue is selected at run time so that the kernel holds ONE copy of the row loop.
+// The epilogue is selected at run time so that the kernel holds ONE copy of the row loops.
 // Every finished element is published at once (st.relaxed {value, epoch}); nothing else marks the end of a phase.
+// Two ways to share the tiles of a phase among the 15 consumer warps:
+//   shared tiles (few rows per CTA: latency matters): every warp works on every tile, rows spread over lane teams;
+//   owned tiles  (many rows per CTA: throughput matters): tile j belongs to warp j % 15, which walks its rows alone
+//                with full-warp K-split dots while the other warps do the same on their tiles.
 template <int QUANT, int LPG>
-__device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r, StCursor &c, const StKind &k, uint32_t epi, uint32_t layer,
+__device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r, StCursor &c, uint32_t &tcount, const StKind &k, uint32_t epi, uint32_t layer,
                                            uint32_t row0, uint32_t rows, uint32_t epoch, const unsigned char *act, uint32_t pos, float pen,
-                                           float *xown, MatvecSmem &ms, unsigned long long *dbg) {
+                                           float *xown, MatvecSmem &ms, const StGeo &geo, uint32_t kid, unsigned long long *dbg) {
     const Dims &d = g.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // lanes per row team and rows per warp pass: Q80 one lane per group (see st_row_q80_lpg); F32 / Q4K one warp per row
-    uint32_t TS = 32u;
-    if (QUANT == 0x80) { const uint32_t G = k.n / (LPG * 16u); TS = G < 32u ? G : 32u; }
-    const uint32_t RW = 32u / TS;
-    const bool pair = (epi == EPI_SWIGLU);                               // a team does both rows of a (w1, w3) pair
-    const uint32_t team = min((uint32_t)lane / TS, RW - 1u), tl = lane % TS, team_base = team * TS;
-    const bool lane_on = (uint32_t)lane < RW * TS;
     float bestv = -FLT_MAX; uint32_t besti = 0xffffffffu;
-    for (uint32_t done = 0; done < rows; done += k.tile_rows) {
-        const uint32_t tr = min(k.tile_rows, rows - done);
-        ST_DBG(5);
-        mbar_wait(&r.full[c.s], c.par, g.err, 0x20u + epi);
-        ST_DBG(6);
-        const unsigned char *tile = r.buf + (size_t)c.s * r.stage_bytes;
-        const unsigned char *aux = tile + (size_t)tr * k.row_stride;
-        const uint32_t step_rows = pair ? 2u * RW : RW;
-        for (uint32_t rb = warp * step_rows; rb < tr; rb += kConsWarps * step_rows) {       // warp-uniform trip count
-            const uint32_t rr = rb + (pair ? 2u * team : team);
-            const bool valid = lane_on && rr < tr;
-            const uint32_t rc = (rr < tr) ? rr : tr - (pair ? 2u : 1u);
-            const uint32_t row = row0 + done + rc;
-            auto one = [&](uint32_t r2) -> float {
-                const unsigned char *wrow = tile + (size_t)r2 * k.row_stride, *ax = aux + (size_t)r2 * k.aux_stride;
-                if constexpr (QUANT == 0x80) return st_row_q80_lpg<LPG>(wrow, reinterpret_cast<const float *>(ax), k.n, act, TS, tl, team_base);
-                else if constexpr (QUANT == 0x42) return st_row_q4k(wrow, ax, k.n, act);
-                else return st_row_f32(wrow, k.n, act);
-            };
-            float v = one(rc), v3 = 0.0f;
-            if (pair) v3 = one(rc + 1u);
-            ST_DBG(7);
-            if (epi == EPI_SWIGLU) {
-                // rows (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
-                if (valid) {
-                    const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
-                    xw_publish(g.xv[2], g.rs[2], row >> 1, __fmul_rn(__fmul_rn(v, sg), v3), epoch, tl, TS);
+    // epilogue of one finished row (value in all `ts` lanes of its team; `ri` = index among the rows this CTA owns)
+    auto emit = [&](uint32_t row, uint32_t ri, float v, float v3, bool pub, uint32_t tl, uint32_t ts) {
+        if (epi == EPI_SWIGLU) {
+            // rows (2i, 2i+1) = (w1 row i, w3 row i); infer.c:937-944
+            if (pub) {
+                const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+                xw_publish(g.xv[2], g.rs[2], row >> 1, __fmul_rn(__fmul_rn(v, sg), v3), epoch, tl, ts);
+            }
+        } else if (epi == EPI_RESID) {
+            const float xn = __fadd_rn(xown[ri], v);                    // infer.c:906, :963
+            __syncwarp();
+            if (pub) {
+                if (tl == 0) xown[ri] = xn;
+                xw_publish(g.xv[0], g.rs[0], row, xn, epoch, tl, ts);
+            }
+        } else if (epi == EPI_QKV) {
+            if (pub && tl == 0) {
+                xw_st(g.xq + row, v, epoch);
+                if (row >= d.q_dim + d.kv_dim) {                         // V rows also go to the cache for later positions
+                    const uint32_t cc = row - d.q_dim - d.kv_dim, h = cc / d.hd, i = cc % d.hd;
+                    g.vc[(size_t)layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + i] = v;
                 }
-            } else if (epi == EPI_RESID) {
-                const uint32_t ri = done + rc;                              // index among the rows this CTA owns
-                const float xn = __fadd_rn(xown[ri], v);                    // infer.c:906, :963
-                __syncwarp();
-                if (valid) {
-                    if (tl == 0) xown[ri] = xn;
-                    xw_publish(g.xv[0], g.rs[0], row, xn, epoch, tl, TS);
+            }
+        } else if (pub) {
+            // classifier: infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037 (rows ascend per lane)
+            if (pen != 1.0f && __ldcg(g.seen + row)) v = __fdiv_rn(v, pen);
+            if (tl == 0) g.logits[row] = v;
+            if (v > bestv) { bestv = v; besti = row; }
+        }
+    };
+    if (k.owned) {
+        // ---- owned tiles ----
+        StCursor cc = c;
+        uint32_t j = 0;
+        for (uint32_t done = 0; done < rows; done += k.tile_rows, j++) {
+            if (j % kConsWarps == (uint32_t)warp) {
+                const uint32_t tr = min(k.tile_rows, rows - done), want = tcount + j;
+                if (r.tile_id[cc.s] != want) {
+                    const long long t0 = clock64();
+                    while (r.tile_id[cc.s] != want) { if (clock64() - t0 > 4000000000ll) st_give_up(g.err, 0x28u); }
                 }
-            } else if (epi == EPI_QKV) {
-                if (valid && tl == 0) {
-                    xw_st(g.xq + row, v, epoch);
-                    if (row >= d.q_dim + d.kv_dim) {                         // V rows also go to the cache for later positions
-                        const uint32_t cc = row - d.q_dim - d.kv_dim, h = cc / d.hd, i = cc % d.hd;
-                        g.vc[(size_t)layer * d.KV * d.max_seq * d.hd + ((size_t)h * d.max_seq + pos) * d.hd + i] = v;
+                mbar_wait(&r.full[cc.s], cc.par, g.err, 0x29u);
+                const unsigned char *tile = r.buf + (size_t)cc.s * r.stage_bytes;
+                const unsigned char *aux = tile + (size_t)tr * k.row_stride;
+                for (uint32_t rr = 0; rr < tr; rr += 2u) {
+                    const bool two = rr + 1u < tr;
+                    const uint32_t r1 = two ? rr + 1u : rr;
+                    float v[2];
+                    if constexpr (QUANT == 0x80) {
+                        if (two) st_rows_q80_warp<LPG, 2>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v);
+                        else { float v1[1]; st_rows_q80_warp<LPG, 1>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v1); v[0] = v1[0]; v[1] = 0.0f; }
+                    } else if constexpr (QUANT == 0x42) {
+                        v[0] = st_row_q4k(tile + (size_t)rr * k.row_stride, aux + (size_t)rr * k.aux_stride, k.n, act);
+                        v[1] = two ? st_row_q4k(tile + (size_t)r1 * k.row_stride, aux + (size_t)r1 * k.aux_stride, k.n, act) : 0.0f;
+                    } else {
+                        v[0] = st_row_f32(tile + (size_t)rr * k.row_stride, k.n, act);
+                        v[1] = two ? st_row_f32(tile + (size_t)r1 * k.row_stride, k.n, act) : 0.0f;
+                    }
+                    if (epi == EPI_SWIGLU) emit(row0 + done + rr, done + rr, v[0], v[1], true, (uint32_t)lane, 32u);
+                    else {
+                        emit(row0 + done + rr, done + rr, v[0], 0.0f, true, (uint32_t)lane, 32u);
+                        if (two) emit(row0 + done + r1, done + r1, v[1], 0.0f, true, (uint32_t)lane, 32u);
                     }
                 }
-            } else if (valid) {
-                // classifier: infer.c:1156-1167 penalty (division, any sign), then first-max argmax :1026-1037 (rows ascend per team)
-                if (pen != 1.0f && __ldcg(g.seen + row)) v = __fdiv_rn(v, pen);
-                if (tl == 0) g.logits[row] = v;
-                if (v > bestv) { bestv = v; besti = row; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_n(&r.empty[cc.s], kConsWarps);      // the only consumer of this stage
             }
+            st_advance(cc, r.nstages);
         }
-        ST_DBG(8);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&r.empty[c.s]);
-        st_advance(c, r.nstages);
+        c = cc; tcount += j;
+    } else {
+        // ---- shared tiles: lanes per row team and rows per warp pass from the table computed at kernel start ----
+        const uint32_t TS = geo.ts[kid], RW = geo.rw[kid], mode = geo.mode[kid], lg2 = geo.lg2[kid], gteam = geo.gteam[kid];
+        const uint32_t team = geo.team[kid][lane], tl = geo.tl[kid][lane], team_base = team * TS, gl = geo.gl[kid][lane], ul = geo.ul[kid][lane];
+        const bool lane_on = (uint32_t)lane < RW * TS;
+        for (uint32_t done = 0; done < rows; done += k.tile_rows) {
+            const uint32_t tr = min(k.tile_rows, rows - done);
+            ST_DBG(5);
+            mbar_wait(&r.full[c.s], c.par, g.err, 0x20u + epi);
+            ST_DBG(6);
+            const unsigned char *tile = r.buf + (size_t)c.s * r.stage_bytes;
+            const unsigned char *aux = tile + (size_t)tr * k.row_stride;
+            // rows of a warp pass: mode 0 one row per team; mode 1 the teams 2t, 2t+1 do the two rows of a pair; mode 2 a team does both
+            const uint32_t step_rows = (mode == 2u) ? 2u * RW : RW;
+            for (uint32_t rb = warp * step_rows; rb < tr; rb += kConsWarps * step_rows) {       // warp-uniform trip count
+                const uint32_t rr = rb + (mode == 2u ? 2u * team : team);
+                const bool valid = lane_on && rr < tr;
+                const uint32_t rc = (rr < tr) ? rr : tr - 1u;
+                auto one = [&](uint32_t r2) -> float {
+                    const unsigned char *wrow = tile + (size_t)r2 * k.row_stride, *ax = aux + (size_t)r2 * k.aux_stride;
+                    if constexpr (QUANT == 0x80) return st_row_q80_lpg<LPG>(wrow, reinterpret_cast<const float *>(ax), k.n, act, lg2, gteam, gl, ul, team_base, dbg);
+                    else if constexpr (QUANT == 0x42) return st_row_q4k(wrow, ax, k.n, act);
+                    else return st_row_f32(wrow, k.n, act);
+                };
+                float v = one(rc), v3 = 0.0f;
+                bool pub = valid;                                                 // does this team publish the element?
+                if (mode == 2u) v3 = one(min(rc + 1u, tr - 1u));
+                else if (mode == 1u) { v3 = __shfl_sync(0xffffffffu, v, (lane + TS) & 31u); pub = valid && !(team & 1u); }
+                ST_DBG(7);
+                emit(row0 + done + rc, done + rc, v, v3, pub, tl, TS);
+            }
+            ST_DBG(8);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r.empty[c.s]);
+            st_advance(c, r.nstages);
+            tcount++;
+        }
     }
     ST_DBG(9);
     if (epi == EPI_CLS) {
 #pragma unroll
-        for (uint32_t o = 1u; o < 32u; o <<= 1) {                          // first max over the lanes (= teams) of the warp
+        for (uint32_t o = 1u; o < 32u; o <<= 1) {                          // first max over the lanes of the warp
             const float ov = __shfl_xor_sync(0xffffffffu, bestv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, besti, o);
             if (oi != 0xffffffffu && (besti == 0xffffffffu || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
         }
@@ -544,10 +672,11 @@ __device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r,
 // A range held by one item is normalised and published at once; otherwise every item publishes its partial and the item
 // of split 0 merges them in split order.
 template <int KVM>
-static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCursor &c, uint32_t layer, uint32_t cta, uint32_t pos, uint32_t range,
-                                    uint32_t nsplit, uint32_t chunk, uint32_t e_in, uint32_t e_out, float *sm) {
+static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCursor &c, uint32_t &tcount, uint32_t layer, uint32_t cta, uint32_t pos, uint32_t range,
+                                    uint32_t nsplit, uint32_t chunk, uint32_t e_in, uint32_t e_out, float *sm, unsigned long long *dbg) {
     const Dims &d = g.d;
     if (cta >= d.KV * nsplit) return;
+    ST_DBG(0);
     const uint32_t hd = d.hd, hd4 = hd / 4u;
     const uint32_t kvh = cta / nsplit, sp = cta % nsplit;
     const uint32_t t0 = min(range, sp * chunk), t1 = min(range, t0 + chunk);
@@ -567,7 +696,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
     float *q_s = sm;                                   // [KVM][hd]   normalised + RoPE'd query heads
     float *S = q_s + KVM * hd;                         // [KVM][seg_max] scores, then probabilities
     float *st_scale = S + KVM * seg_max;               // [KVM] e^{m_old - m_new} of the current segment
-    float *krow = st_scale + KVM;                      // [hd] the position's k (post-RoPE), [hd] the position's v
+    float *krow = st_scale + ((KVM + 3) & ~3);         // [hd] the position's k (post-RoPE), [hd] the position's v (16-byte aligned)
     float *outp = krow + 2 * hd;                       // [KVM][hd + 2]: acc, M, L
 
     // ---- this step's q / k / v: warp m < KVM prepares query head m, warp KVM the k row, warp KVM + 1 the v row ----
@@ -598,6 +727,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
     float m_run = -FLT_MAX, l_run = 0.0f;
     float acc[2] = {0.0f, 0.0f};
     cbar();
+    ST_DBG(1);
 
     for (uint32_t s0 = t0; s0 < t1; s0 += seg_max) {
         const uint32_t rows_seg = min(seg_max, t1 - s0), nt = (rows_seg + kvr - 1u) / kvr;
@@ -605,7 +735,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
 #pragma unroll
         for (int i = 0; i < kStSegTiles; i++) {
             stg[i] = 0;
-            if ((uint32_t)i < nt) { mbar_wait(&r.full[c.s], c.par, g.err, 0x30u); stg[i] = c.s; st_advance(c, r.nstages); }
+            if ((uint32_t)i < nt) { mbar_wait(&r.full[c.s], c.par, g.err, 0x30u); stg[i] = c.s; st_advance(c, r.nstages); tcount++; }
         }
         auto tile_k = [&](uint32_t ti) -> float * {
             uint32_t sidx = stg[0];
@@ -613,8 +743,9 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
             for (int i = 1; i < kStSegTiles; i++) if (ti == (uint32_t)i) sidx = stg[i];
             return reinterpret_cast<float *>(r.buf + (size_t)sidx * r.stage_bytes);
         };
+        ST_DBG(2);
         if (owns && pos >= s0 && pos < s0 + rows_seg) {     // CTA-uniform: this step's k / v into their slots of the resident tile
-            const uint32_t pr = pos - s0, ti = pr / kvr, rr = pr % kvr;
+            const uint32_t pr = pos - s0, ti = __umulhi(pr, g.kv_tile_magic), rr = pr - ti * kvr;
             float *kt = tile_k(ti);
             for (uint32_t i = threadIdx.x; i < hd; i += kConsThreads) {
                 kt[(size_t)rr * hd + i] = krow[i];
@@ -622,26 +753,33 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
             }
             cbar();
         }
-        // ---- scores ----
-        for (uint32_t idx = threadIdx.x; idx < rows_seg; idx += kConsThreads) {
-            const uint32_t ti = idx / kvr, rr = idx - ti * kvr;
-            const float *kr = tile_k(ti) + (size_t)rr * hd;
-            float a[KVM];
-#pragma unroll
-            for (int m = 0; m < KVM; m++) a[m] = 0.0f;
-            for (uint32_t cc = 0; cc < hd4; cc++) {
-                uint32_t ch = cc + idx; ch -= (ch / hd4) * hd4;
-                const float4 k4 = *reinterpret_cast<const float4 *>(kr + ch * 4u);
-#pragma unroll
-                for (int m = 0; m < KVM; m++) {
-                    const float4 q4 = *reinterpret_cast<const float4 *>(q_s + m * hd + ch * 4u);
-                    a[m] = fmaf(k4.x, q4.x, fmaf(k4.y, q4.y, fmaf(k4.z, q4.z, fmaf(k4.w, q4.w, a[m]))));
+        ST_DBG(3);
+        // ---- scores: task = (row, head, quarter of the dims); the 4 lanes of a task take interleaved 16-byte chunks (rotated by
+        //      the row index: conflict-free although rows are a multiple of 128 bytes apart) and combine with two shuffles ----
+        {
+            const uint32_t ntask = rows_seg * KVM;                 // (row, head) pairs; 4 lanes each
+            const uint32_t part = threadIdx.x & 3u;
+            for (uint32_t t4 = threadIdx.x >> 2; t4 < ((ntask + 7u) & ~7u); t4 += kConsThreads / 4u) {       // warp-uniform trip count (8 tasks per warp)
+                const bool on = t4 < ntask;
+                const uint32_t tc = on ? t4 : 0u;
+                const uint32_t idx = tc / KVM, m = tc - idx * KVM;
+                const uint32_t ti = __umulhi(idx, g.kv_tile_magic), rr = idx - ti * kvr;
+                const float *kr = tile_k(ti) + (size_t)rr * hd;
+                const float *qm = q_s + m * hd;
+                float a = 0.0f;
+                const uint32_t rot = (hd4 & 3u) ? 0u : 4u * (idx & 7u);       // rotation keeps the 4 lanes' chunk sets disjoint only if hd % 16 == 0
+                for (uint32_t cc = part; cc < hd4; cc += 4u) {
+                    uint32_t ch = cc + rot; while (ch >= hd4) ch -= hd4;
+                    const float4 k4 = *reinterpret_cast<const float4 *>(kr + ch * 4u), q4 = *reinterpret_cast<const float4 *>(qm + ch * 4u);
+                    a = fmaf(k4.x, q4.x, fmaf(k4.y, q4.y, fmaf(k4.z, q4.z, fmaf(k4.w, q4.w, a))));
                 }
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                if (on && part == 0) S[m * seg_max + idx] = __fdiv_rn(a, dv);         // infer.c:858
             }
-#pragma unroll
-            for (int m = 0; m < KVM; m++) S[m * seg_max + idx] = __fdiv_rn(a[m], dv);         // infer.c:858
         }
         cbar();
+        ST_DBG(4);
         // ---- online softmax over the segment: warp m owns head m ----
         if (warp < KVM) {
             float *Sm = S + warp * seg_max;
@@ -658,30 +796,38 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
             if (lane == 0) st_scale[warp] = sc_old;
         }
         cbar();
-        // ---- P.V: thread j owns (head, dim) j ----
+        ST_DBG(5);
+        // ---- P.V: thread j owns (head, dim) j; rows in order, four at a time (probabilities as one float4) ----
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const uint32_t j = threadIdx.x + u * kConsThreads;
             if (j < KVM * hd) {
                 const uint32_t m = j / hd, dd = j - m * hd;
                 const float *Sm = S + m * seg_max;
-                float a = acc[u] * st_scale[m];
+                float a0 = acc[u] * st_scale[m], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
                 for (uint32_t ti = 0; ti < nt; ti++) {
                     const float *vt = tile_k(ti) + (size_t)kvr * hd + dd;
                     const uint32_t nr = min(kvr, rows_seg - ti * kvr);
-                    const float *sp2 = Sm + ti * kvr;
-#pragma unroll 4
-                    for (uint32_t rr = 0; rr < nr; rr++) a = fmaf(sp2[rr], vt[(size_t)rr * hd], a);
+                    const float *sp2 = Sm + ti * kvr;                   // kvr % 4 == 0: 16-byte aligned
+                    uint32_t rr = 0;
+                    for (; rr + 4u <= nr; rr += 4u) {
+                        const float4 p4 = *reinterpret_cast<const float4 *>(sp2 + rr);
+                        a0 = fmaf(p4.x, vt[(size_t)rr * hd], a0); a1 = fmaf(p4.y, vt[(size_t)(rr + 1u) * hd], a1);
+                        a2 = fmaf(p4.z, vt[(size_t)(rr + 2u) * hd], a2); a3 = fmaf(p4.w, vt[(size_t)(rr + 3u) * hd], a3);
+                    }
+                    for (; rr < nr; rr++) a0 = fmaf(sp2[rr], vt[(size_t)rr * hd], a0);
                 }
-                acc[u] = a;
+                acc[u] = (a0 + a1) + (a2 + a3);
             }
         }
         cbar();
+        ST_DBG(6);
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < kStSegTiles; i++) if ((uint32_t)i < nt) mbar_arrive(&r.empty[stg[i]]);
         }
     }
+    ST_DBG(7);
     // ---- the item's partial: per head [acc[hd], M, L] ----
 #pragma unroll
     for (int u = 0; u < 2; u++) {
@@ -691,6 +837,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
     if (warp < KVM && lane == 0) { outp[warp * (hd + 2) + hd] = m_run; outp[warp * (hd + 2) + hd + 1] = l_run; }
     const uint32_t pw = KVM * (hd + 2);                               // words of one partial
     cbar();
+    ST_DBG(8);
     if (nsplit == 1) {          // the whole range in one item: normalise and publish
         for (uint32_t e = threadIdx.x; e < KVM * hd * (uint32_t)kStRep; e += kConsThreads) {
             const uint32_t el = e / kStRep, rep = e % kStRep, m = el / hd, i = el % hd;
@@ -703,6 +850,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
         for (uint32_t idx = threadIdx.x; idx < pw; idx += kConsThreads) xw_st(part + (size_t)sp * pw + idx, outp[idx], e_out);
         return;
     }
+    ST_DBG(9);
     // ---- merge (split 0): own partial from shared memory, the others polled from the exchange words ----
     uint32_t region = st_attn_work_floats(KVM, hd, seg_max);
     if (g.nsplit_max * KVM * hd > region) region = g.nsplit_max * KVM * hd;
@@ -722,11 +870,18 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
     };
 #pragma unroll
     for (int u = 0; u < 4; u++) { const uint32_t idx = threadIdx.x + u * kConsThreads; if (idx < pw) place(0, idx, own[u]); }
-    for (uint32_t e = pw + threadIdx.x; e < nsplit * pw; e += kConsThreads) {
-        const uint32_t s2 = e / pw, idx = e % pw;
-        place(s2, idx, xw_poll1(part + (size_t)s2 * pw + idx, e_out, g.err));
+    for (uint32_t e0 = pw + threadIdx.x; e0 < nsplit * pw; e0 += 8u * kConsThreads) {       // eight loads in flight per thread before any epoch is checked
+        unsigned long long w8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const uint32_t e = e0 + u * kConsThreads; if (e < nsplit * pw) w8[u] = xw_ld1(part + e); }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t e = e0 + u * kConsThreads;
+            if (e < nsplit * pw) place(e / pw, e % pw, xw_ok(w8[u], e_out) ? xw_val(w8[u]) : xw_poll1(part + e, e_out, g.err));
+        }
     }
     cbar();
+    ST_DBG(10);
     if (warp < KVM) {
         float pm[2], pls[2];                             // nsplit_max <= 64: two slots per lane
 #pragma unroll
@@ -753,6 +908,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
         for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(macc[(m * nsplit + s2) * hd + i], wsc[m * g.nsplit_max + s2], o);
         xw_st(g.xv[1] + (size_t)rep * g.rs[1] + ((size_t)kvh * KVM + m) * hd + i, __fdiv_rn(o, stat[m]), e_out);
     }
+    ST_DBG(11);
 }
 
 // ---------------------------------------------------------------- grid barrier, once per token (consumer warps; the producer keeps streaming)
@@ -782,8 +938,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
     __syncthreads();
     const StreamArgs &g = sg;
     __shared__ uint64_t full_bar[kStMaxStages], empty_bar[kStMaxStages];
+    __shared__ volatile uint32_t stage_tile[kStMaxStages];
     __shared__ MatvecSmem ms;
     __shared__ StOwn own;
+    __shared__ StGeo geo;
     __shared__ float xown[kStOwnMax];
     __shared__ volatile uint32_t s_progress;
     __shared__ unsigned int s_target;
@@ -791,9 +949,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
     const uint32_t cta = blockIdx.x, ncta = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    StRing ring{full_bar, empty_bar, ssm + g.off_ring, g.nstages, g.stage_bytes};
+    StRing ring{full_bar, empty_bar, stage_tile, ssm + g.off_ring, g.nstages, g.stage_bytes};
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsWarps); }
+        for (uint32_t s = 0; s < g.nstages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsWarps); stage_tile[s] = 0xffffffffu; }
         s_progress = 0; s_target = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -801,6 +959,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
         const StKind &k = g.kind[threadIdx.x];
         const uint32_t u0 = (uint32_t)(((uint64_t)cta * k.units) / ncta), u1 = (uint32_t)(((uint64_t)(cta + 1) * k.units) / ncta);
         own.row0[threadIdx.x] = u0 * k.unit_rows; own.rows[threadIdx.x] = (u1 - u0) * k.unit_rows;
+        // how a warp shares the rows of this kind: the candidate with the cheapest (passes x estimated chain latency)
+        const uint32_t kid = threadIdx.x, rows = (u1 - u0) * k.unit_rows;
+        uint32_t b_lg2 = 1, b_gt = 32, b_ts = 32, b_rw = 1, b_mode = (kid == SK_W13) ? 2u : 0u;
+        if (QUANT == 0x80) {
+            const uint32_t G = k.n / (LPG * 16u);
+            uint32_t best = 0xffffffffu;
+            for (uint32_t cand = LPG; cand >= 1u; cand >>= 1) {
+                if (G * cand > 32u && cand > 1u) continue;
+                const uint32_t gt = G < 32u / cand ? G : 32u / cand, t = gt * cand, rw = 32u / t;
+                const uint32_t md = (kid == SK_W13) ? ((rw >= 2u && !(rw & 1u)) ? 1u : 2u) : 0u;
+                const uint32_t per_pass = kConsWarps * (md == 2u ? 2u * rw : rw);
+                const uint32_t tr = rows < k.tile_rows ? rows : k.tile_rows, ntl = tr ? (rows + k.tile_rows - 1u) / k.tile_rows : 0u;
+                const uint32_t passes = ntl * ((tr + per_pass - 1u) / (per_pass ? per_pass : 1u));
+                uint32_t lat = 300u + ((G + gt - 1u) / gt) * (80u * (LPG / cand) + 35u * (31u - __clz(cand)) + 120u + 5u * gt);
+                if (md == 2u) lat *= 2u;
+                const uint32_t cost = passes * lat;
+                if (cost < best) { best = cost; b_lg2 = cand; b_gt = gt; b_ts = t; b_rw = rw; b_mode = md; }
+            }
+        }
+        geo.lg2[kid] = (uint8_t)b_lg2; geo.gteam[kid] = (uint8_t)b_gt; geo.ts[kid] = (uint8_t)b_ts; geo.rw[kid] = (uint8_t)b_rw; geo.mode[kid] = (uint8_t)b_mode;
+    }
+    __syncthreads();
+    if (threadIdx.x < 160) {
+        const uint32_t kid = threadIdx.x >> 5, ln = threadIdx.x & 31u, ts = geo.ts[kid], rw = geo.rw[kid], lg2 = geo.lg2[kid];
+        const uint32_t tm = ln / ts, tl = ln % ts;
+        geo.team[kid][ln] = (uint8_t)(tm < rw ? tm : rw - 1u); geo.tl[kid][ln] = (uint8_t)tl;
+        geo.gl[kid][ln] = (uint8_t)(tl / lg2); geo.ul[kid][ln] = (uint8_t)(tl % lg2);
     }
     __syncthreads();
 
@@ -821,6 +1006,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
     const uint32_t rep = cta % (uint32_t)kStRep;                       // the replica this CTA reads
     const unsigned long long *rx = g.xv[0] + (size_t)rep * g.rs[0], *rxba = g.xv[1] + (size_t)rep * g.rs[1], *rhb = g.xv[2] + (size_t)rep * g.rs[2];
     StCursor cur{0u, 0u};
+    uint32_t tcount = 0;                                                // tiles consumed so far (the producer counts the same way)
     uint32_t ti = 0, tj = 0;
     // stamps (trace != nullptr: CTA 0 / thread 0, last step): [0..] after every phase; [1024..] inside layer L/2
 #define ST_TRACE() do { if (g.trace && cta == 0 && threadIdx.x == 0 && step + 1 == g.n_steps && ti < 1000) g.trace[ti++] = clock64(); } while (0)
@@ -857,11 +1043,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
                 else { xsrc = rhb; need = el + 4u; epi = EPI_RESID; eout = el + 5u; }
                 unsigned long long *dbg = (g.trace && cta == 0 && step + 1 == g.n_steps && l == d.L / 2) ? g.trace + 1100 + 16 * ph : nullptr;
                 if (own.rows[kid]) {          // CTA-uniform: a CTA without rows of this kind neither reads the source nor publishes
-#pragma unroll 1
-                    for (uint32_t again = 0; again < (dbg ? 2u : 1u); again++)          // trace launches run the prologue twice: cold vs hot instruction cache
-                        st_prep<QUANT, LPG>(g, xsrc, ssrc, need, gain, k.n, act, ms.red, (dbg && again) ? g.trace + 1200 + 16 * ph : dbg);
+                    st_prep<QUANT, LPG>(g, xsrc, ssrc, need, gain, k.n, act, ms.red, dbg);
                     ST_STAMP();
-                    st_consume<QUANT, LPG>(g, ring, cur, k, epi, l, own.row0[kid], own.rows[kid], eout, act, pos, pen, xown, ms, dbg);
+                    st_consume<QUANT, LPG>(g, ring, cur, tcount, k, epi, l, own.row0[kid], own.rows[kid], eout, act, pos, pen, xown, ms, geo, kid, dbg);
+                    cbar();        // the next phase (prologue or attention) overwrites the activation operand the slowest warp may still be reading
                 } else {
                     ST_STAMP();
                     if (cls && lane == 0) { ms.best_v[warp] = -FLT_MAX; ms.best_i[warp] = 0xffffffffu; }
@@ -870,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
                 ST_TRACE();
                 if (cls) break;
                 if (ph == SK_QKV) {
-                    st_attention<KVM>(g, ring, cur, l, cta, pos, range, nsplit, chunk, el + 1u, el + 2u, attn_ws);
+                    st_attention<KVM>(g, ring, cur, tcount, l, cta, pos, range, nsplit, chunk, el + 1u, el + 2u, attn_ws, dbg ? g.trace + 1100 + 64 : nullptr);
                     cbar();                                              // the attention workspace aliases the activation operand
                     ST_STAMP();
                     ST_TRACE();

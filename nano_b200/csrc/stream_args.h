@@ -22,13 +22,13 @@ struct StKind {               // geometry of one matvec phase kind (identical fo
     uint32_t n;               // row length in elements
     uint32_t row_stride;      // bytes between rows inside a tile (row bytes + 16)
     uint32_t aux_stride;      // bytes between aux rows inside a tile (Q80: scales, Q4K: side records; 0 for F32)
-    uint32_t pad;
+    uint32_t owned;           // 1: throughput mode, every tile is consumed by ONE warp (tile j -> warp j % 15); 0: all warps share a tile
 };
 
 struct StreamArgs {
     const uint8_t *stream; uint64_t cta_stride, layer_stride, cls_off;
     StKind kind[5];
-    uint32_t nstages, stage_bytes, kv_tile_rows;
+    uint32_t nstages, stage_bytes, kv_tile_rows, kv_tile_magic;      // magic = ceil(2^32 / kv_tile_rows): idx / kv_tile_rows == umulhi(idx, magic) for idx < 65536
     uint32_t off_ring, off_act, off_xs, off_attn;     // byte offsets inside dynamic shared memory
     const float *g_attn, *g_ffn, *g_final;            // rmsnorm gains [L][E], [L][E], [E]
     const float *qnorm, *knorm, *rope_cos, *rope_sin;
@@ -51,18 +51,18 @@ struct StreamArgs {
 
 // activation prologue: warp slots held in registers between the sum-of-squares pass and the quantise pass; the host
 // checks n <= st_prep_max_n before choosing the streaming kernel
-constexpr int kStKmax = 6, kStKmaxQ4K = 2;
+constexpr int kStKmax = 3, kStKmaxQ4K = 2;           // warp slots of 256 elements
 __host__ __device__ inline uint32_t st_prep_max_n(uint32_t quant, uint32_t gs) {
     (void)gs;
-    return quant == 0x42u ? (uint32_t)kConsWarps * kStKmaxQ4K * 256u : (uint32_t)kConsWarps * kStKmax * 128u;
+    return quant == 0x42u ? (uint32_t)kConsWarps * kStKmaxQ4K * 256u : (uint32_t)kConsWarps * kStKmax * 256u;
 }
 
 // attention workspace of one CTA (floats): q [KVM][hd] | scores of a segment [KVM][seg rows] | per-head scale [KVM] |
 // the position's k, v [2][hd] | the item's partial [KVM][hd + 2]; the merge of a multi-split head stages the partials of
 // all splits in the same region, followed by the merge weights / partial sums [2][KVM][nsplit_max] and totals [KVM]
-constexpr int kStSegTiles = 4;                    // ring tiles of K/V that an attention segment keeps resident
+constexpr int kStSegTiles = 8;                    // ring tiles of K/V that an attention segment keeps resident
 __host__ __device__ inline uint32_t st_attn_work_floats(uint32_t kvm, uint32_t hd, uint32_t seg_rows) {
-    return kvm * hd + kvm * seg_rows + kvm + 2u * hd + kvm * (hd + 2u) + 16u;
+    return kvm * hd + kvm * seg_rows + ((kvm + 3u) & ~3u) + 2u * hd + kvm * (hd + 2u) + 16u;
 }
 __host__ __device__ inline uint32_t st_attn_smem_floats(uint32_t kvm, uint32_t hd, uint32_t nsplit_max, uint32_t seg_rows) {
     uint32_t ws = st_attn_work_floats(kvm, hd, seg_rows);

@@ -88,6 +88,13 @@ PRESETS: Dict[str, ModelSpec] = {
     "toy-qwen3": ModelSpec("toy-qwen3", ARCH_QWEN3, 128, 2048, 2, 256, 4, 2, 512, 64),
     "mini-qwen3": ModelSpec("mini-qwen3", ARCH_QWEN3, 256, 4096, 4, 512, 8, 4, 1024, 128),
     "mini-nano": ModelSpec("mini-nano", ARCH_NANO, 256, 2048, 4, 768, 16, 8, 2048),
+    # loader branches: untied Q80 classifier (infer.c:206-216) and the Qwen2 architecture (infer.c:175-179: biases parsed, never applied)
+    "toy-nano-untied": ModelSpec("toy-nano-untied", ARCH_NANO, 64, 512, 2, 256, 4, 2, 512, 0, 0),
+    "toy-qwen3-untied": ModelSpec("toy-qwen3-untied", ARCH_QWEN3, 128, 2048, 2, 256, 4, 2, 512, 64, 0),
+    "toy-qwen2": ModelSpec("toy-qwen2", ARCH_QWEN2, 64, 512, 2, 256, 4, 2, 512),
+    # long-context shapes (2 layers of the Nano-168M / Qwen3-0.6B layer shape): attention with many splits and segments
+    "long-nano": ModelSpec("long-nano", ARCH_NANO, 4096, 2048, 2, 768, 16, 8, 2048),
+    "long-qwen3": ModelSpec("long-qwen3", ARCH_QWEN3, 4096, 4096, 2, 1024, 16, 8, 3072, 128),
 }
 
 
@@ -279,7 +286,14 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
             c, s = _rope_table(spec.block_size, hd)
             f.write(c.tobytes()); f.write(s.tobytes())
         # arch 3: the reference rebuilds its table (infer.c:189-204) and never reads one from the file;
-        # Q4K arch-3 files end right after k_norm (tools/export_q4k.c:176-204). Nothing is written.
+        # Q4K arch-3 files end right after k_norm (tools/export_q4k.c:176-204). Nothing is written -- unless an untied
+        # classifier follows: the reference steps over a table-sized gap first (infer.c:201-202).
+        if not spec.tied:
+            assert quant == QUANT_Q80, "untied classifier: Q80 only (infer.c:206-216; the F32 pointer is a reference bug, Q4K is always tied)"
+            if spec.arch == ARCH_QWEN3:
+                f.write(np.zeros(2 * spec.block_size * (hd // 2), dtype=np.float32).tobytes())
+            q, s = quantize_q80(normal(V * E, std * cls_gain).reshape(V, E), gs)
+            f.write(q.tobytes()); f.write(s.tobytes())
         size = f.tell()
     return {"path": path, "bytes": size, "spec": spec, "quant": quant, "gs": gs}
 

@@ -129,7 +129,7 @@ const uint8_t *orh_sort_model(uint32_t *len) {
     return SORT_6_MODEL;
 }
 
-/* layout report used by tests/test_abi_layout.py to pin include/nano_infer_abi.h */
+/* layout report used by tests/test_boundary.py to pin include/nano_infer_abi.h */
 #include <stddef.h>
 #define ORH_OFF(T, f) out[n++] = (uint32_t)offsetof(T, f)
 uint32_t orh_abi_layout(uint32_t *out, uint32_t cap) {

@@ -1,0 +1,43 @@
+"""GPU parity on the BASELINE model shapes themselves: Nano-168M Q80 (24 layers) and Qwen3-0.6B Q80 / Q4K
+(28 layers, V = 151 936), 40 teacher-forced positions against the strict oracle: logits within the fast-mode policy, greedy ids
+agreeing wherever the oracle's margin is real (margins printed), on the default execution path of each model.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from nano_b200 import engine as E, modelfile as mf
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+# name, quant, gs, committed floor of the reference's own fast-vs-strict deviation on this shape
+CASES = [("nano-168m", mf.QUANT_Q80, 128, 4.5e-2), ("qwen3-0.6b", mf.QUANT_Q80, 128, 4.5e-2), ("qwen3-0.6b", mf.QUANT_Q4K, 128, 0.45)]
+
+
+@pytest.mark.parametrize("name,quant,gs,floor", CASES)
+def test_baseline_shape_logits_and_ids(name, quant, gs, floor):
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S = 40
+    eng = E.Engine(path, S)
+    o = ob.NanoOracle(path, S)
+    ob.NanoOracle.lib().nor_set_threads(min(32, os.cpu_count() or 1))
+    toks = mf.teacher_tokens(S, spec.vocab)
+    limit = max(1e-2, 1.5 * floor)
+    worst, agree, real, margins = 0.0, 0, 0, []
+    for pos in range(S):
+        a = eng.forward(toks[pos], pos); b = o.forward(toks[pos], pos)
+        worst = max(worst, float(np.abs(a - b).max()))
+        top2 = np.partition(b, -2)[-2:]
+        m = float(top2[1] - top2[0]); margins.append(m)
+        same = int(np.argmax(a)) == int(np.argmax(b))
+        agree += same
+        if m > 2 * limit:
+            real += 1
+            assert same, f"{name} pos {pos}: argmax differs although the oracle margin is {m}"
+    print(f"{name} {quant:#x} [{eng.path[:24]}]: max|dlogit| {worst:.3e} (limit {limit:.3e}), argmax agreement {agree}/{S}, "
+          f"{real} positions with a decisive margin, median margin {np.median(margins):.3e}")
+    assert worst <= limit, f"{name} {quant:#x}: {worst} > {limit}"
+    eng.close(); o.close()

@@ -64,7 +64,7 @@ def reference_noise_floor(name, quant, gs, path, S):
     return floor
 
 
-@pytest.mark.parametrize("path_flags", [0, E.FLAG_NO_STREAM], ids=["stream", "multikernel"])
+@pytest.mark.parametrize("path_flags", [0, -1, E.FLAG_NO_STREAM], ids=["stream", "stream-owned-tiles", "multikernel"])
 @pytest.mark.parametrize("name,quant,gs", TOY)
 def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags, monkeypatch):
     """Fast mode (parallel fp32 reductions): within the north-star tolerance, or -- where the reference's own
@@ -74,6 +74,8 @@ def test_teacher_forced_logits_fast_mode(name, quant, gs, path_flags, monkeypatc
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S = 40
+    if path_flags == -1:      # the streaming kernel's throughput mode (one warp per tile), which toy shapes would not reach by themselves
+        monkeypatch.setenv("NB200_OWNED_ROWS", "2"); path_flags = 0
     eng = E.Engine(path, S, flags=path_flags); o = ob.NanoOracle(path, S)
     toks = mf.teacher_tokens(S, spec.vocab)
     floor = reference_noise_floor(name, quant, gs, path, S)
@@ -185,6 +187,38 @@ def test_greedy_ids_exact_mode_and_device_loop(name, quant, gs, penalty, monkeyp
     if min(runs[0][1], runs[1][1]) > 2 * limit:
         assert runs[0][0] == runs[1][0]
     o.close()
+
+
+@pytest.mark.parametrize("name", ["toy-nano-untied", "toy-qwen3-untied", "toy-qwen2"])
+def test_loader_branches_untied_classifier_and_qwen2(name):
+    """memory_map_params branches no shipped model uses (infer.c:175-179 Qwen2 biases parsed and skipped; :206-216 separate Q80
+    classifier after the RoPE tables / the RoPE gap): exact mode bit-identical to the oracle, fast paths within tolerance."""
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, mf.QUANT_Q80, 64)
+    S = 16
+    o = ob.NanoOracle(path, S)
+    engs = [E.Engine(path, S, flags=E.FLAG_EXACT), E.Engine(path, S), E.Engine(path, S, flags=E.FLAG_NO_STREAM)]
+    assert engs[0].tied == spec.tied
+    toks = mf.teacher_tokens(S, spec.vocab)
+    for pos in range(S):
+        ref = o.forward(toks[pos], pos)
+        assert_bits_equal(engs[0].forward(toks[pos], pos), ref, f"{name} pos {pos}")
+        for e2 in engs[1:]:
+            assert np.abs(e2.forward(toks[pos], pos) - ref).max() <= 3e-2
+    for e2 in engs:
+        e2.close()
+    o.close()
+
+
+def test_rejects_untied_f32_and_truncated_files():
+    spec = mf.PRESETS["toy-qwen2"]
+    img = open(mf.cached_model(spec, mf.QUANT_Q80, 64), "rb").read()
+    with pytest.raises(E.NB200Error):
+        E.Engine(img[: len(img) - 4096], 8)          # truncated inside the RoPE tables that follow the Qwen2 biases
+    f32 = bytearray(open(mf.cached_model(mf.PRESETS["toy-nano"], mf.QUANT_F32, 128), "rb").read())
+    f32[52:56] = (0).to_bytes(4, "little")          # is_shared_classifier = 0 on an F32 file: the reference's pointer for it is wrong
+    with pytest.raises(E.NB200Error):
+        E.Engine(bytes(f32), 8)
 
 
 def test_activation_codes_dump_bit_exact():

@@ -1,0 +1,77 @@
+"""GPU parity at the BASELINE sequence lengths: teacher-forced runs of 512 / 2048 / 4096 positions against
+the oracle on every execution path.  Two-layer models of the Nano-168M / Qwen3-0.6B layer shape keep the CPU oracle affordable;
+the attention sees exactly the shapes of the benched runs (8 kv heads, head_dim 48 / 128, up to 18 splits per kv head, several
+ring segments per split, the multi-split merge).
+
+  exact mode (multi-kernel path)   : logits and K/V rows bit-identical to the strict oracle
+  fast mode, streaming + multi-kernel: within max(1e-2, 1.5 x the reference's own fast-vs-strict floor) and argmax agreement wherever
+                                     the oracle's top-1/top-2 margin exceeds twice that
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+from nano_b200 import engine as E, modelfile as mf
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("long-nano", 128, 512), ("long-qwen3", 128, 2048), ("long-qwen3", 128, 4096)]
+
+
+def _floor(name, path, n):
+    """the reference's own -O3 -ffast-math vs strict deviation on the first n positions of this file (when oracle/_ref travelled)"""
+    fl = ob.best_fast_flavour()
+    if not (fl and ob.ref_available("strict")):
+        return 0.0
+    a = ob.RefEngine(path, n, "strict"); b = ob.RefEngine(path, n, fl)
+    toks = mf.teacher_tokens(n, mf.PRESETS[name].vocab)
+    worst = 0.0
+    for pos in range(n):
+        worst = max(worst, float(np.abs(a.forward(toks[pos], pos) - b.forward(toks[pos], pos)).max()))
+    a.close(); b.close()
+    return worst
+
+
+@pytest.mark.parametrize("name,gs,S", CASES)
+def test_long_sequence_parity_all_paths(name, gs, S, monkeypatch):
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, mf.QUANT_Q80, gs)
+    monkeypatch.setenv("NB200_STREAM", "1")                    # the streaming kernel even where it is not the default for the size
+    o = ob.NanoOracle(path, S)
+    ob.NanoOracle.lib().nor_set_threads(min(32, os.cpu_count() or 1))
+    engines = {"stream": E.Engine(path, S), "multikernel": E.Engine(path, S, flags=E.FLAG_NO_STREAM),
+               "exact": E.Engine(path, S, flags=E.FLAG_EXACT)}
+    assert engines["stream"].path.startswith("streaming"), engines["stream"].path
+    toks = mf.teacher_tokens(S, spec.vocab)
+    limit = max(1e-2, 1.5 * _floor(name, path, 64))
+    check = set(range(0, 6)) | set(range(7, S, 61)) | {S // 2, S - 2, S - 1}
+    worst = {k: 0.0 for k in engines}
+    for pos in range(S):
+        ref = o.forward(toks[pos], pos)
+        for k, eng in engines.items():
+            if pos not in check:
+                eng.forward_nolog(toks[pos], pos)
+                continue
+            lg = eng.forward(toks[pos], pos)
+            if k == "exact":
+                assert_bits_equal(lg, ref, f"{name} S={S} exact pos {pos}")
+                continue
+            dlt = float(np.abs(lg - ref).max())
+            worst[k] = max(worst[k], dlt)
+            top2 = np.partition(ref, -2)[-2:]
+            if float(top2[1] - top2[0]) > 2 * limit:
+                assert int(np.argmax(lg)) == int(np.argmax(ref)), f"{k} pos {pos}: argmax differs with margin {top2[1] - top2[0]}"
+    ok, ov = o.kv()
+    for l in range(spec.n_layer):
+        for pos in (0, S // 3, S - 1):
+            assert_bits_equal(engines["exact"].read(E.F_KROW, spec.kv_dim, l, pos), ok[l, pos], "K row")
+            assert_bits_equal(engines["exact"].read(E.F_VROW, spec.kv_dim, l, pos), ov[l, pos], "V row")
+    print(f"{name} S={S}: max|dlogit| stream {worst['stream']:.3e} multikernel {worst['multikernel']:.3e} (limit {limit:.3e})")
+    for k in ("stream", "multikernel"):
+        assert worst[k] <= limit, f"{name} S={S} {k}: {worst[k]} > {limit}"
+    for eng in engines.values():
+        eng.close()
+    o.close()

@@ -91,3 +91,7 @@ def test_tp_rejects_bad_shapes_and_unattached_use():
     with pytest.raises(E.NB200Error):
         lone.forward(1, 0)                  # peers never attached
     lone.close()
+    # 14 q heads on 2 kv heads (n_head / n_kv_head = 7): no tensor-parallel attention kernel for that ratio -> rejected at creation
+    odd = mf.ModelSpec("odd-gqa", mf.ARCH_QWEN3, 64, 512, 1, 256, 14, 2, 512, 64)
+    with pytest.raises(E.NB200Error):
+        E.Engine(mf.cached_model(odd, mf.QUANT_F32, 128), 16, tp=(0, 2))

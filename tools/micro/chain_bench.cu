@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(512, 1) k_chain(const float *xin, unsigned lon
     for (int i = threadIdx.x; i < 16 * 2080 / 4; i += 480) reinterpret_cast<uint32_t *>(tile)[i] = 0x03fe01ffu * (i + 3);
     cbar();
     float4 v = reinterpret_cast<const float4 *>(xin)[threadIdx.x];
-    long long tA = 0, tB = 0, tB2 = 0, tC6 = 0, tC16 = 0, tD = 0;
+    long long tA = 0, tB = 0, tB2 = 0, tC6 = 0, tC16 = 0, tD = 0, tV[4] = {0, 0, 0, 0};
     float sink = 0.0f;
     for (int it = 0; it < iters + 2; it++) {
         const bool on = it >= 2;
@@ -114,6 +114,43 @@ __global__ void __launch_bounds__(512, 1) k_chain(const float *xin, unsigned lon
             t1 = clock64();
             if (on) { if (G == 6) tC6 += t1 - t0; else tC16 += t1 - t0; }
         }
+        // ---- C2..C5: lane-per-group variants (6 groups, 5 rows per warp) ----
+        for (int var = 0; var < 4; var++) {
+            cbar();
+            t0 = clock64();
+            const uint32_t TS = 6, tl = lane % TS, team = min((uint32_t)lane / TS, 4u), team_base = team * TS;
+            const unsigned char *wrow = tile + (size_t)((warp * 5 + team) % 16) * 2080;
+            const float *srow = reinterpret_cast<const float *>(act + 2048), *xs = reinterpret_cast<const float *>(act + 2048 + 64);
+            const unsigned char *wp = wrow + tl * 128, *xp = act + tl * 128;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const uint32_t off = ((uint32_t)(c + tl) % 8) * 16u;
+                const int4 w = *reinterpret_cast<const int4 *>(wp + off), xq = *reinterpret_cast<const int4 *>(xp + off);
+                a0 = __dp4a(w.x, xq.x, a0); a1 = __dp4a(w.y, xq.y, a1); a2 = __dp4a(w.z, xq.z, a2); a3 = __dp4a(w.w, xq.w, a3);
+            }
+            float val = 0.0f;
+            if (var == 0) {            // C2: as in the kernel (runtime-count shuffle loop)
+                const float term = __fmul_rn(__fmul_rn((float)((a0 + a1) + (a2 + a3)), srow[tl]), xs[tl]);
+                const uint32_t cnt = min(TS, (uint32_t)(6 + (it >> 20)));
+                for (uint32_t j = 0; j < cnt; j++) val = __fadd_rn(val, __shfl_sync(0xffffffffu, term, team_base + j));
+            } else if (var == 1) {     // C3: unrolled-by-8 predicated shuffle gather
+                const float term = __fmul_rn(__fmul_rn((float)((a0 + a1) + (a2 + a3)), srow[tl]), xs[tl]);
+                const uint32_t cnt = min(TS, (uint32_t)(6 + (it >> 20)));
+                float t8[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) t8[j] = __shfl_sync(0xffffffffu, term, team_base + j);
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((uint32_t)j < cnt) val = __fadd_rn(val, t8[j]);
+            } else if (var == 2) {     // C4: no gather at all (integer sum -> float)
+                val = __fmul_rn(__fmul_rn((float)((a0 + a1) + (a2 + a3)), srow[tl]), xs[tl]);
+            } else {                   // C5: loads + dp4a only
+                val = __int_as_float((a0 + a1) + (a2 + a3));
+            }
+            sink += val;
+            t1 = clock64();
+            if (on) tV[var] += t1 - t0;
+        }
         // ---- D ----
         t0 = clock64();
         {
@@ -129,7 +166,7 @@ __global__ void __launch_bounds__(512, 1) k_chain(const float *xin, unsigned lon
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         out[0] = tA / iters; out[1] = tB / iters; out[2] = tB2 / iters; out[3] = tC6 / iters; out[4] = tC16 / iters; out[5] = tD / iters;
-        out[7] = (long long)sink;
+        out[7] = (long long)sink; for (int i = 0; i < 4; i++) out[8 + i] = tV[i] / iters;
     }
 }
 
@@ -143,9 +180,10 @@ int main() {
     for (int ncta : {1, 148}) {
         k_chain<<<ncta, 512>>>(x, words, out, 200);
         CK(cudaDeviceSynchronize());
-        long long r[8]; CK(cudaMemcpy(r, out, 64, cudaMemcpyDeviceToHost));
+        long long r[12]; CK(cudaMemcpy(r, out, 96, cudaMemcpyDeviceToHost));
         printf("ncta=%3d  A inverse(block reduce) %lld | B quantise group %lld | B2 redux+branch-free %lld | C row dot 6 groups %lld, 16 groups %lld | D poll4 ready %lld  cycles\n",
                ncta, r[0], r[1], r[2], r[3], r[4], r[5]);
+        printf("          lane-per-group row dot (6 groups): C2 runtime shuffle loop %lld | C3 unrolled gather %lld | C4 no gather %lld | C5 loads+dp4a only %lld\n", r[8], r[9], r[10], r[11]);
     }
     return 0;
 }
