@@ -12,12 +12,17 @@ from oracle import bindings as ob
 
 pytestmark = pytest.mark.gpu
 
-# name, quant, gs, committed floor of the reference's own fast-vs-strict deviation on this shape
-CASES = [("nano-168m", mf.QUANT_Q80, 128, 4.5e-2), ("qwen3-0.6b", mf.QUANT_Q80, 128, 4.5e-2), ("qwen3-0.6b", mf.QUANT_Q4K, 128, 0.45)]
+# The floor = the reference's own -O3 -ffast-math vs strict deviation on the same file over the same 40 positions, measured with the
+# unmodified reference in the build container and committed in tests/golden/reference_noise_floor.json (Qwen3-0.6B Q4K: 0.83, with the
+# reference's two builds agreeing on only 27 of 40 greedy ids -- SURVEY finding 11 at full scale).
+CASES = [("nano-168m", mf.QUANT_Q80, 128), ("qwen3-0.6b", mf.QUANT_Q80, 128), ("qwen3-0.6b", mf.QUANT_Q4K, 128)]
 
 
-@pytest.mark.parametrize("name,quant,gs,floor", CASES)
-def test_baseline_shape_logits_and_ids(name, quant, gs, floor):
+@pytest.mark.parametrize("name,quant,gs", CASES)
+def test_baseline_shape_logits_and_ids(name, quant, gs):
+    import json
+    from conftest import GOLDEN
+    floor = json.load(open(os.path.join(GOLDEN, "reference_noise_floor.json")))[f"{name}_{quant:02x}_{gs}"]
     spec = mf.PRESETS[name]
     path = mf.cached_model(spec, quant, gs)
     S = 40
