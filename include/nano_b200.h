@@ -17,6 +17,8 @@
  *   nb200_read_logits     <- FwdBuffer.logits       infer/infer.h:139 (host float* in the reference)
  *   nb200_next_greedy     <- generate_next_token    infer/infer.c:1135-1193 (temperature == 0 branch:
  *                            repetition penalty :1156-1167 + sample_argmax :1026-1037)
+ *   nb200_next_sampled    <- generate_next_token    infer/infer.c:1156-1189 (temperature > 0: softmax :616-634,
+ *                            sample_top_p :1062-1109 with the caller's xorshift coin utils.c:959-970)
  *   nb200_decode_greedy   <- the llm_session_step loop of infer/infer.c:1243-1310 with the token fed back
  *                            on the device (no host round trip per token)
  *   nb200_op_*            <- rmsnorm :601, matmul :637, matmul_quant :654 (infer/infer.c); quantize tensor.c:21,
@@ -125,6 +127,14 @@ int nb200_read_logits(nb200_engine *e, float *host_logits);
  * and ids[pos+1] is returned (infer.c:1146-1149). */
 int nb200_next_greedy(nb200_engine *e, const uint32_t *ids, uint32_t pos, int is_prefilling,
                       float repetition_penalty, uint32_t *next_token);
+
+/* generate_next_token with temperature > 0 (infer/infer.c:1156-1189), entirely on the device: repetition penalty, division by the
+ * temperature, softmax (:616-634, sequential normaliser), cutoff filter, probability-descending order with ties in index order
+ * (what glibc's stable qsort gives `compare` :1053-1059), cumulative top-p cut and CDF walk (sample_top_p :1062-1109).
+ * `coin` is the caller's random_f32(&sampler->rng_state) draw (utils.c:959-970).  Returns the sampled id and, if top6 != NULL, the
+ * six most probable ids (what the reference hands its observation hook).  32 bytes come back instead of vocab_size * 4. */
+int nb200_next_sampled(nb200_engine *e, const uint32_t *ids, uint32_t pos, float repetition_penalty, float temperature, float top_p,
+                       float coin, uint32_t *next_token, uint32_t *top6);
 
 /* Device-resident greedy loop: ids[0..n_prompt) is the prompt; positions 0..n_total-2 are run and
  * ids[n_prompt..n_total) are filled with greedy tokens (prompt positions are teacher-forced exactly like

@@ -28,6 +28,7 @@
 #include "../../include/nano_b200.h"
 #include "kernels.cuh"
 #include "stream_host.h"
+#include "sample_host.h"
 
 using namespace nb;
 
@@ -104,6 +105,7 @@ struct nb200_engine {
     bool use_stream = false; const void *st_kern = nullptr; StreamArgs sa{}; uint32_t st_smem = 0, st_grid = 0;
     uint32_t *st_err_host = nullptr, *st_err_dev = nullptr;      // mapped pinned word: the code a device-side spin recorded before trapping
     uint32_t st_epoch = 0;                                       // exchange epochs handed out so far (stream.cuh)
+    void *samp_ws = nullptr; size_t samp_cub = 0; uint32_t *samp_host = nullptr;       // device-side sampler workspace (sample.cu), pinned result
     uint64_t stream_bytes = 0;
     unsigned int *bar = nullptr;
     uint64_t launches = 0, weight_bytes = 0;
@@ -646,6 +648,7 @@ void nb200_engine_destroy(nb200_engine *e) {
     for (void *p : e->tp_ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : e->allocs) cudaFree(p);
     if (e->st_host) cudaFreeHost(e->st_host);
+    if (e->samp_host) cudaFreeHost(e->samp_host);
     if (e->tok_host) cudaFreeHost(e->tok_host);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1149,6 +1152,34 @@ int nb200_next_greedy(nb200_engine *e, const uint32_t *ids, uint32_t pos, int is
     CK(cudaStreamSynchronize(e->stream));
     *next = is_prefilling ? ids[pos + 1] : *e->tok_host;
     return tp_check(e);
+}
+
+/* nb200_next_sampled <- generate_next_token, temperature > 0 branch (infer.c:1156-1189: penalty, /= temperature, softmax, coin, sample_top_p).
+ * The whole step runs on the device; `coin` is the host's random_f32 draw.  top6 (optional): the six most probable ids (observation hook). */
+int nb200_next_sampled(nb200_engine *e, const uint32_t *ids, uint32_t pos, float penalty, float temperature, float top_p, float coin,
+                       uint32_t *next, uint32_t *top6) {
+    if (!e || !ids || !next) return fail(NB200_EINVAL, "null argument");
+    if (pos >= e->d.max_seq || ids[pos] >= e->d.V) return fail(NB200_EINVAL, "token/pos out of range");
+    if (!(temperature > 0.0f)) return fail(NB200_EINVAL, "temperature must be > 0 (use nb200_next_greedy for 0)");
+    if (e->tp_size > 1) return fail(NB200_EINVAL, "device-side sampling is not available on tensor-parallel engines (logits are sharded)");
+    CK(cudaSetDevice(e->device));
+    if (!e->samp_ws) {
+        const size_t bytes = sample_workspace_bytes(e->d.V, &e->samp_cub);
+        DM(e->samp_ws, bytes);
+        CK(cudaHostAlloc(&e->samp_host, 64, cudaHostAllocDefault));
+    }
+    int r;
+    if ((r = push_state(e, pos, 1, 0, 0, penalty, ids[pos], 1))) return r;
+    if (penalty != 1.0f) { if ((r = sync_seen(e, ids, pos))) return r; }
+    if ((r = launch_token(e))) return r;
+    uint32_t *out_dev = nullptr;
+    CK(sample_top_p_launch(e->samp_ws, e->samp_cub, e->logits, e->d.V, temperature, top_p, coin, e->st, &out_dev, e->stream));
+    e->launches += 3;
+    CK(cudaMemcpyAsync(e->samp_host, out_dev, 32, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    *next = e->samp_host[0];
+    if (top6) for (int i = 0; i < 6; i++) top6[i] = e->samp_host[1 + i];
+    return 0;
 }
 
 int nb200_decode_greedy(nb200_engine *e, uint32_t *ids, uint32_t n_prompt, uint32_t n_total, float penalty,

@@ -296,7 +296,27 @@ uint32_t generate_next_token(Nano_Context *ctx, uint32_t *output_ids, uint32_t p
         if (nb200_next_greedy(e, output_ids, pos, is_prefilling == 1, sp->repetition_penalty, &next) != NB200_OK) die("generate_next_token");
         return next;
     }
-    /* temperature > 0: logits come to the host and the reference's sampler runs there (infer.c:1156-1189) */
+    /* temperature > 0 (infer.c:1156-1189): penalty, temperature, softmax, cutoff, ordered top-p all on the device; the coin is the
+     * Sampler's own xorshift draw; 32 bytes come back.  NB200_HOST_SAMPLER=1 keeps the host restatement (logits D2H) for comparison. */
+    const char *hs = getenv("NB200_HOST_SAMPLER");
+    const int host_sampler = (hs && atoi(hs) != 0) ? 1 : 0;
+    if (!host_sampler) {
+        notify_forward(ctx);
+        if (nb200_lora_enable(e, ctx->lora != NULL) != NB200_OK) die("generate_next_token (use_lora)");
+        const float coin = random_f32(&sp->rng_state);
+        uint32_t next = 0, top6[6];
+        if (nb200_next_sampled(e, output_ids, pos, sp->repetition_penalty, sp->temperature, sp->top_p, coin, &next, top6) != NB200_OK) die("generate_next_token (sampling)");
+        if (ctx->observation) {
+            Nano_Observation o;
+            memset(&o, 0, sizeof o);
+            o.layer = -1; o.phase = NANO_PH_SAMPLE;
+            ctx->observation(o, ctx->observation_env);                      /* infer.c:1152 */
+            uint32_t *t = &o.token_0;
+            for (int i = 0; i < 6; i++) t[i] = top6[i];
+            ctx->observation(o, ctx->observation_env);                      /* infer.c:1086-1096 */
+        }
+        return next;
+    }
     float *logits = llm_forward(ctx, output_ids[pos], pos, ctx->max_seq_len, 1, llm, ctx->lora);
     notify(ctx, -1, NANO_PH_SAMPLE);
     const uint32_t V = (uint32_t)sp->vocab_size;

@@ -23,7 +23,7 @@ F_X, F_XBA, F_HB, F_Q, F_LOGITS, F_KROW, F_VROW, F_ACT_I8, F_ACT_SCALE = 0, 2, 4
 
 EXPORTS = [
     "nb200_last_error", "nb200_device_count", "nb200_engine_create", "nb200_engine_destroy", "nb200_get_config",
-    "nb200_forward", "nb200_read_logits", "nb200_next_greedy", "nb200_decode_greedy", "nb200_read_buffer",
+    "nb200_forward", "nb200_read_logits", "nb200_next_greedy", "nb200_next_sampled", "nb200_decode_greedy", "nb200_read_buffer",
     "nb200_write_x", "nb200_run_layer", "nb200_profile_tokens", "nb200_trace_token", "nb200_read_attn_trace", "nb200_kernel_launches", "nb200_launches_per_token", "nb200_weight_bytes",
     "nb200_op_rmsnorm", "nb200_op_q80_quantize", "nb200_op_q80_matvec", "nb200_op_f32_matvec",
     "nb200_op_q4k_quantize", "nb200_op_q4k_matvec",
@@ -66,6 +66,7 @@ def lib():
         L.nb200_forward.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.nb200_read_logits.argtypes = [C.c_void_p, f32p]
         L.nb200_next_greedy.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_int, C.c_float, u32p]
+        L.nb200_next_sampled.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, u32p, u32p]
         L.nb200_decode_greedy.argtypes = [C.c_void_p, u32p, C.c_uint32, C.c_uint32, C.c_float, f32p, f32p]
         L.nb200_read_buffer.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
         L.nb200_write_x.argtypes = [C.c_void_p, f32p, C.c_uint32]
@@ -199,6 +200,12 @@ class Engine:
         nxt = C.c_uint32(0)
         _check(lib().nb200_next_greedy(self.h, _p(ids, u32p), pos, prefilling, penalty, C.byref(nxt)))
         return int(nxt.value)
+
+    def next_sampled(self, ids: np.ndarray, pos: int, penalty: float, temperature: float, top_p: float, coin: float):
+        """generate_next_token with temperature > 0, sampled on the device; returns (token, six most probable ids)."""
+        nxt = C.c_uint32(0); top6 = (C.c_uint32 * 6)()
+        _check(lib().nb200_next_sampled(self.h, _p(ids, u32p), pos, penalty, temperature, top_p, coin, C.byref(nxt), top6))
+        return int(nxt.value), list(top6)
 
     def decode_greedy(self, ids: np.ndarray, n_prompt: int, n_total: int, penalty: float = 1.0) -> Tuple[float, float]:
         """Device-resident loop; fills ids[n_prompt:n_total] in place. Returns (prefill_ms, decode_ms)."""

@@ -89,13 +89,17 @@ def test_generate_next_token_greedy_matches_reference(penalty, monkeypatch):
 
 @needs_refhost
 @pytest.mark.skipif(not ob.ref_available("strict"), reason="needs the unmodified reference for the sampling path")
-def test_temperature_sampling_matches_reference(monkeypatch):
-    """temperature 0.7 / top-p 0.8 (main_cli.c:227): logits go to the host and the reference's sampler is restated
-    there with the reference's own xorshift coin -- same ids as the reference when the logits are bit-identical."""
+@pytest.mark.parametrize("host_sampler", ["0", "1"], ids=["device-sampler", "host-sampler"])
+@pytest.mark.parametrize("name,quant,gs", [("toy-nano", mf.QUANT_Q80, 64), ("mini-qwen3", mf.QUANT_Q80, 128)])
+def test_temperature_sampling_matches_reference(name, quant, gs, host_sampler, monkeypatch):
+    """temperature 0.7 / top-p 0.8 (main_cli.c:227) over 60 (toy-nano) / 96 (mini-qwen3) sampled steps: with bit-identical logits (exact mode) and the reference's own xorshift
+    coin, the ids equal the unmodified strict reference's -- for the device-side sampler (softmax, cutoff, stable descending order,
+    sequential top-p scan on the GPU; 32 bytes back per token) and for the host restatement (NB200_HOST_SAMPLER=1, logits D2H)."""
     monkeypatch.setenv("NB200_EXACT", "1")
-    spec = mf.PRESETS["toy-nano"]
-    path = mf.cached_model(spec, mf.QUANT_Q80, 64)
-    S, P = 28, 4
+    monkeypatch.setenv("NB200_HOST_SAMPLER", host_sampler)
+    spec = mf.PRESETS[name]
+    path = mf.cached_model(spec, quant, gs)
+    S, P = min(100, spec.block_size), 4            # never beyond the model's RoPE table
     L = shim()
     ctx = L.llm_context_init(path.encode(), None, S, 1.1, 0.7, 0.8, 20, 39)
     ref = ob.RefEngine(path, S, "strict", penalty=1.1, temperature=0.7, top_p=0.8, top_k=20, seed=39)
@@ -107,6 +111,7 @@ def test_temperature_sampling_matches_reference(monkeypatch):
         ids[pos + 1] = L.generate_next_token(ctx, ids, pos, pre)
         want[pos + 1] = ref.next(want, pos, pre)
     assert list(ids)[:S] == want[:S].tolist()
+    assert len(set(list(ids)[P:S])) > 20          # it really sampled: not a constant stream
     L.llm_context_free(ctx)
 
 
