@@ -350,7 +350,7 @@ def measure(E, workload, steps, warmup, local, dist=None, world=1, flags=0, e2e=
     wall = barrier_max(dist, local, wall)
     value = aggregate_tokens_per_s(world, steps, n_dec, dec_ms)
     res = {"value": value, "ms_per_step": wall * 1e3 / steps, "gpu_launches": int(launches), "launches_per_token": eng.launches_per_token,
-           "engine": eng.path, "dec_ms": dec_ms}
+           "engine": eng.path, "path_calibration": eng.calibration, "dec_ms": dec_ms}
     timed_ids = ids.copy()
 
     if e2e:
@@ -457,12 +457,20 @@ def tp_block(E, rank, world, local, dist):
         _p1, dec1 = one.decode_greedy(ids1, PROMPT, seq)
         path1 = one.path
         one.close()
+        dflt = E.Engine(path, seq, device=local)               # the one-GPU engine a user gets by default (path chosen by calibration)
+        ids2 = prompt_ids(spec, seq)
+        dflt.decode_greedy(ids2, PROMPT, seq)
+        ids2 = prompt_ids(spec, seq)
+        _p2, dec2 = dflt.decode_greedy(ids2, PROMPT, seq)
+        path2, calib2 = dflt.path, dflt.calibration
+        dflt.close()
         tp_tok, one_tok = n_dec / (dec * 1e-3), n_dec / (dec1 * 1e-3)
         nx = 4 * spec.n_layer + 1
         out = {"workload": workload_config(TP_WORKLOAD)["workload"], "n_gpus": world, "scaling": "strong",
                "parallelism": f"tp{world}: one batch-1 session; every weight matrix row-sharded over {world} GPUs (QKV and the KV cache by kv head); "
                               f"{nx} activation exchanges per token pushed into every rank's copy through NVLink peer memory from inside the kernels (no NCCL on the data path)",
                "value": tp_tok, "unit": "tokens/s", "one_gpu_same_path": one_tok, "one_gpu_engine": path1, "speedup_vs_one_gpu": tp_tok / one_tok,
+               "one_gpu_default": {"value": n_dec / (dec2 * 1e-3), "engine": path2, "path_calibration": calib2},
                "exchanges_per_token": nx,
                "per_exchange_us_model": ((dec / n_dec) - (dec1 / n_dec) / world) * 1e3 / nx,
                "per_exchange_note": "(ms/token at tp - ms/token on one GPU / N) / exchanges: what an exchange costs beyond perfectly divided streaming time",
@@ -545,7 +553,7 @@ def main():
                 continue
             try:
                 r = measure(E, w, 2, 1, local, flags=flags)
-                extra[w] = {"config": workload_config(w), "value": r["value"], "unit": "tokens/s", "e2e": r.get("e2e"), "engine": r["engine"],
+                extra[w] = {"config": workload_config(w), "value": r["value"], "unit": "tokens/s", "e2e": r.get("e2e"), "engine": r["engine"], "path_calibration": r.get("path_calibration"),
                             "gpu_launches": r["gpu_launches"], "roofline": {k: v for k, v in (r.get("roofline") or {}).items() if k != "per_kernel"},
                             "token_roofline": r["token_roofline"], "parity": r.get("parity"), "dtype": DTYPE[WORKLOADS[w][1]]}
             except Exception as ex:
@@ -561,7 +569,7 @@ def main():
         "vs_baseline": None, "dtype": DTYPE[quant], "data": "synthetic",
         "config": workload_config(args.workload),
         "run": {"parallelism": f"{world} independent batch-1 session(s), one per GPU, no data-path collective", "mode": "exact" if args.exact else "fast",
-                "engine": res["engine"],
+                "engine": res["engine"], "path_calibration": res.get("path_calibration"),
                 "value_path": "device-resident greedy loop (nb200_decode_greedy); the drop-in per-token number is e2e"},
         "clocks": clocks, "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"], "launches_per_token": res["launches_per_token"],
         "roofline": res.get("roofline"), "token_roofline": res["token_roofline"], "parity": res.get("parity"),

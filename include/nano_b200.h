@@ -63,7 +63,8 @@ typedef struct nb200_config {
     uint32_t block_size, vocab_size, n_layer, n_embd, n_head, n_kv_head, n_hidden, tied, head_dim;
     uint32_t q_dim, kv_dim, max_seq_len;
     uint32_t tp_rank, tp_size;
-    uint32_t reserved[7];
+    uint32_t reserved[7];   /* [0] execution path: 4 streaming kernel, 1 CUDA graph, 0 direct launches; [1], [2] creation-time calibration:
+                               us per token of the streaming kernel / of the multi-kernel graph (0 = the choice was not measured) */
 } nb200_config;
 
 /* fields readable with nb200_read_buffer (same numbering as oracle probes) */

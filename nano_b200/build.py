@@ -63,6 +63,21 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
     return ENGINE_SO
 
 
+TRACE_SO = os.path.join(LIB, "libnano_b200_trace.so")
+
+
+def build_trace_variant() -> str:
+    """Developer build of the streaming kernel with its fine cycle stamps compiled in (-DNB200_FINE_TRACE; they cost ~200
+    cycles each, so the product library never carries them).  Loaded by tools/gpu_trace.py through NB200_ENGINE_SO."""
+    build_engine()
+    obj = os.path.join(LIB, "stream_trace.o")
+    subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+                    "-DNB200_FINE_TRACE", "-c", os.path.join(CSRC, "stream.cu"), "-o", obj], check=True)
+    objs = [os.path.join(LIB, u[:-3] + ".o") for u in UNITS if u != "stream.cu"] + [obj]
+    subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", TRACE_SO] + objs, check=True)
+    return TRACE_SO
+
+
 def build_shim(force: bool = False) -> str:
     src = os.path.join(CSRC, "infer_b200.c")
     hdrs = [os.path.join(ROOT, "include", "nano_infer_abi.h"), os.path.join(ROOT, "include", "nano_b200.h")]

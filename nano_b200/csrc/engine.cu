@@ -102,6 +102,7 @@ struct nb200_engine {
     bool use_pdl = true;
     unsigned long long *trace_dev = nullptr;
     // grid-wide persistent streaming kernel (stream.cuh): the default path in fast mode on one GPU
+    float calib_ms[2] = {0.0f, 0.0f};      // ms per token of {streaming, multi-kernel} measured by calibrate_paths (0 = not calibrated)
     bool use_stream = false; const void *st_kern = nullptr; StreamArgs sa{}; uint32_t st_smem = 0, st_grid = 0;
     uint32_t *st_err_host = nullptr, *st_err_dev = nullptr;      // mapped pinned word: the code a device-side spin recorded before trapping
     uint32_t st_epoch = 0;                                       // exchange epochs handed out so far (stream.cuh)
@@ -514,11 +515,34 @@ int setup_stream(nb200_engine *e) {
         const uint32_t ub = km[i].unit * (sk.row_stride + sk.aux_stride);
         if (ub > unit_b_max) unit_b_max = ub;
     }
-    // ring stage: at least two row units of the longest row, 16 KB by default
+    // shared-memory plan: [activation operand 0 | activation operand 1 | embedding row | attention workspace | ring].  Nothing aliases, so a
+    // phase never waits for the slowest warp of the previous one before it writes its operand.  The ring stage is 16 KB by default and
+    // shrinks in 1 KB steps (never below one row unit of the longest row) until kStSegTiles + 4 stages fit beside the fixed regions.
+    auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
+    const uint32_t nsplit_max = e->nsplit_max;          // num_sms / kv heads (<= 64), as the multi-kernel path
+    const uint32_t act_b = al(act_region_bytes(d.quant, maxn, d.gs ? d.gs : 1));
+    g.off_act = 0; g.off_act2 = act_b; g.off_xs = 2 * act_b; g.off_attn = g.off_xs + al(d.E * 4u);
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, (const void *)k));
+    const uint32_t static_smem = al((uint32_t)fattr.sharedSizeBytes);   // mbarriers, row ranges, residual rows, reduction scratch
+    const uint32_t min_stage = (unit_b_max + 16u + 1023u) & ~1023u;
     uint32_t stage_bytes = env_u32("NB200_STAGE_KB", 16) * 1024u;
-    if (stage_bytes < 2 * unit_b_max + 16u) stage_bytes = (2 * unit_b_max + 16u + 1023u) & ~1023u;
-    uint32_t kv_rows = (stage_bytes / (2u * d.hd * 4u)) & ~3u;
-    if (kv_rows < 4) return 0;
+    if (stage_bytes < min_stage) stage_bytes = min_stage;
+    const uint32_t nst_cap = env_u32("NB200_STAGES", kStMaxStages) < (uint32_t)kStMaxStages ? env_u32("NB200_STAGES", kStMaxStages) : (uint32_t)kStMaxStages;
+    uint32_t kv_rows = 0, region0 = 0, nst = 0;
+    for (;; stage_bytes -= 1024u) {
+        kv_rows = (stage_bytes / (2u * d.hd * 4u)) & ~3u;
+        if (kv_rows < 4) return 0;
+        const uint32_t attn_b = al(st_attn_smem_floats(d.kv_mul, d.hd, nsplit_max, (uint32_t)kStSegTiles * kv_rows) * 4u);
+        region0 = g.off_attn + attn_b;
+        nst = (uint32_t)max_optin > static_smem + region0 ? ((uint32_t)max_optin - static_smem - region0) / stage_bytes : 0u;
+        if (nst > nst_cap) nst = nst_cap;
+        if (nst >= (uint32_t)kStSegTiles + 4u) break;   // an attention segment keeps kStSegTiles tiles resident while the next ones arrive
+        if (stage_bytes < min_stage + 1024u) return 0;
+    }
+    g.off_ring = region0;
     uint64_t off = 0;
     uint32_t ntl[5];
     for (int i = 0; i < 5; i++) {
@@ -550,23 +574,6 @@ int setup_stream(nb200_engine *e) {
     g.kind[SK_CLS].off = 0;
     g.cta_stride = (g.cls_off + (uint64_t)ntl[SK_CLS] * g.kind[SK_CLS].tile_stride + 127u) & ~(uint64_t)127u;
 
-    // shared-memory plan: [activation operand | embedding row] aliased with the attention workspace, then the ring
-    auto al = [](uint32_t v) { return (v + 127u) & ~127u; };
-    const uint32_t nsplit_max = e->nsplit_max;          // num_sms / kv heads (<= 64), as the multi-kernel path
-    const uint32_t act_b = al(act_region_bytes(d.quant, maxn, d.gs ? d.gs : 1));
-    uint32_t region0 = act_b + al(d.E * 4u);
-    const uint32_t attn_b = al(st_attn_smem_floats(d.kv_mul, d.hd, nsplit_max, (uint32_t)kStSegTiles * kv_rows) * 4u);
-    if (attn_b > region0) region0 = attn_b;
-    g.off_act = 0; g.off_xs = act_b; g.off_attn = 0; g.off_ring = region0;
-    int max_optin = 0;
-    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
-    const uint32_t static_smem = 6144;                  // mbarriers, row ranges, residual rows, reduction scratch (static __shared__)
-    if ((uint32_t)max_optin < region0 + static_smem + 3 * stage_bytes) return 0;
-    uint32_t nst = ((uint32_t)max_optin - static_smem - region0) / stage_bytes;
-    const uint32_t nst_cap = env_u32("NB200_STAGES", kStMaxStages);
-    if (nst > nst_cap) nst = nst_cap;
-    if (nst > (uint32_t)kStMaxStages) nst = kStMaxStages;
-    if (nst < (uint32_t)kStSegTiles + 4u) return 0;      // an attention segment keeps kStSegTiles tiles resident while the next ones arrive
     const uint32_t smem = region0 + nst * stage_bytes;
     cudaError_t ce = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
@@ -619,6 +626,7 @@ int setup_stream(nb200_engine *e) {
     g.n_steps = 1; g.nsplit_max = nsplit_max;
     uint32_t ct = 32768u / (d.hd * 8u); ct &= ~7u; if (ct < 32) ct = 32;      // measured: ~32 KB of K+V per (kv head, split) item
     g.chunk_target = env_u32("NB200_ATTN_CHUNK", ct);
+    g.ablate = env_u32("NB200_ABLATE", 0);
     if (g.chunk_target < 8) g.chunk_target = 8;
     g.d = d;
     e->st_kern = (const void *)k; e->st_smem = smem; e->st_grid = NC; e->use_stream = true; e->launches_per_token = 1;
@@ -655,6 +663,9 @@ void nb200_engine_destroy(nb200_engine *e) {
 }
 
 static int finish_paths(nb200_engine *e);
+static int calibrate_paths(nb200_engine *e);
+static int push_state(nb200_engine *e, uint32_t pos, uint32_t causal, uint32_t n_prompt, uint32_t advance, float penalty,
+                      uint32_t token, uint32_t use_token);
 
 static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_bytes, uint32_t max_seq_len, int device,
                        uint32_t flags, uint32_t tp_rank, uint32_t tp_size) {
@@ -912,16 +923,19 @@ static int create_impl(nb200_engine **out, const uint8_t *img, uint64_t image_by
     CK(cudaDeviceSynchronize());
 
     {
-        // Default path in fast mode on one GPU, by measured speed (profiles/r2_paths.md): the streaming kernel for F32 / Q4K models and for
-        // Q80 models under 256 MB of weights (latency-bound: one launch, no per-phase kernel boundary); the CUDA-graph multi-kernel path
-        // for larger Q80 models.  NB200_STREAM=1 forces the streaming kernel where the shape allows it, NB200_STREAM=0 / NB200_FLAG_NO_STREAM forbid it.
+        // Default path in fast mode on one GPU.  The streaming kernel is set up whenever the shape allows it.  F32 / Q4K models and Q80
+        // models under 256 MB of weights always run it (latency-bound: one launch, no kernel boundary per phase).  For larger Q80 models
+        // neither path wins everywhere (profiles/r2_paths.md: multi-kernel ahead at 0.6B / 1.7B, streaming ahead at 4B with a long context),
+        // so the engine times both at the middle of its context and keeps the faster one (calibrate_paths).
+        // NB200_STREAM=1 forces the streaming kernel where the shape allows it, NB200_STREAM=0 / NB200_FLAG_NO_STREAM forbid it.
         const char *st_env = getenv("NB200_STREAM");
         const bool st_forced = st_env && atoi(st_env) == 1, st_off = (st_env && atoi(st_env) == 0) || (flags & NB200_FLAG_NO_STREAM);
-        const bool st_default = d.quant != 0x80u || e->weight_bytes < (256ull << 20);
-        if (T == 1 && !st_off && (st_default || st_forced)) { if ((r = setup_stream(e))) return r; }
+        if (T == 1 && !st_off) { if ((r = setup_stream(e))) return r; }
+        e->path_stream = e->use_stream;
+        if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
+        const bool st_always = d.quant != 0x80u || e->weight_bytes < (256ull << 20);
+        if (e->use_stream && !st_forced && !st_always && (r = calibrate_paths(e))) return r;
     }
-    e->path_stream = e->use_stream;
-    if (T == 1 && (r = finish_paths(e))) return r;      // tensor-parallel engines capture after the peers are attached
     guard.ok = true;
     *out = e;
     return 0;
@@ -941,6 +955,43 @@ static int finish_paths(nb200_engine *e) {
     } else {
         e->launches_per_token = 2 + (5 + (e->lora.active ? 4u : 0u)) * e->d.L;
     }
+    return 0;
+}
+
+// Both fast paths are ready: time `n` decode steps on each from the middle of the context (device loop, CUDA events on the engine's
+// stream, one untimed round first) and keep the faster.  The steps write K/V rows at positions pos0.. -- every later step rewrites its
+// own position before reading it -- and leave no other state behind (push_state precedes every public entry point).
+static int calibrate_paths(nb200_engine *e) {
+    const uint32_t n = 8;
+    if (e->d.max_seq < 4 * n) return 0;
+    const uint32_t pos0 = e->d.max_seq / 2;
+    struct Events { cudaEvent_t ev[2] = {nullptr, nullptr}; ~Events() { for (auto v : ev) if (v) cudaEventDestroy(v); } } evs;
+    for (auto &v : evs.ev) CK(cudaEventCreate(&v));
+    float ms[2] = {0.0f, 0.0f};
+    int r;
+    for (int path = 0; path < 2; path++) {
+        e->use_stream = (path == 0);
+        if (path == 1) { e->launches_per_token = 0; if ((r = finish_paths(e))) return r; }      // captures the multi-kernel graph
+        for (int rep = 0; rep < 2; rep++) {
+            CK(cudaMemsetAsync(e->ids_dev, 0, (size_t)(pos0 + 1) * 4, e->stream));
+            if ((r = push_state(e, pos0, 1, pos0 + 1, 1, 1.0f, 0, 0))) return r;
+            CK(cudaEventRecord(evs.ev[0], e->stream));
+            if (e->use_stream) { if ((r = launch_stream(e, n))) return r; }
+            else for (uint32_t i = 0; i < n; i++) if ((r = launch_token(e))) return r;
+            CK(cudaEventRecord(evs.ev[1], e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+            CK(cudaEventElapsedTime(&ms[path], evs.ev[0], evs.ev[1]));
+        }
+    }
+    e->calib_ms[0] = ms[0] / n; e->calib_ms[1] = ms[1] / n;
+    e->use_stream = ms[0] <= ms[1];
+    e->path_stream = e->use_stream;
+    if (e->use_stream) e->launches_per_token = 1;
+    e->launches = 0;
+    CK(cudaMemsetAsync(e->ids_dev, 0, ((size_t)e->d.max_seq + 8) * 4, e->stream));       // as created
+    CK(cudaMemsetAsync(e->seen, 0, e->d.V, e->stream));
+    e->seen_valid = false; e->seen_mirror.clear();
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -1080,6 +1131,8 @@ int nb200_get_config(const nb200_engine *e, nb200_config *c) {
     c->n_head = e->g_H; c->n_kv_head = e->g_KV; c->n_hidden = d.F; c->tied = e->tied ? 1u : 0u; c->head_dim = d.hd;
     c->q_dim = e->g_q_dim; c->kv_dim = e->g_kv_dim; c->max_seq_len = d.max_seq; c->tp_rank = e->tp_rank; c->tp_size = e->tp_size;
     c->reserved[0] = e->use_stream ? 4u : (e->graph ? 1u : 0u);      // execution path: 4 streaming kernel, 1 graph, 0 direct launches
+    c->reserved[1] = (uint32_t)(e->calib_ms[0] * 1000.0f + 0.5f);     // calibrate_paths: microseconds per token of the streaming kernel ...
+    c->reserved[2] = (uint32_t)(e->calib_ms[1] * 1000.0f + 0.5f);     // ... and of the multi-kernel graph (0 = the choice was not measured)
     return 0;
 }
 

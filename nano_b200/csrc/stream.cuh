@@ -57,14 +57,18 @@ static __device__ __noinline__ void st_give_up(uint32_t *err, uint32_t code) {
     __threadfence_system();
     __trap();
 }
-static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, uint32_t *err, uint32_t code) {
+// A polling warp must not monopolise the SM's MIO pipe (mbarrier, shared-memory and shuffle instructions share it): measured with
+// the producer busy-polling a full ring, a 5-step warp shuffle reduction in a consumer warp took ~1000 cycles instead of ~150.
+// `sleep_ns` > 0: back off between polls (the producer runs ahead of the consumers and is never latency-critical).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity, uint32_t *err, uint32_t code, uint32_t sleep_ns) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (sleep_ns) __nanosleep(sleep_ns);
         if (clock64() - t0 > 4000000000ll) st_give_up(err, code);
     }
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err, uint32_t code) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code);
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err, uint32_t code, uint32_t sleep_ns = 20) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code, sleep_ns);
 }
 // barrier among the 15 consumer warps only (the producer warp never takes part)
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
@@ -81,16 +85,20 @@ __device__ __forceinline__ unsigned long long xw_ld1(const unsigned long long *p
 __device__ __forceinline__ void xw_st(unsigned long long *p, float v, uint32_t epoch) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)epoch << 32) | __float_as_uint(v)) : "memory");
 }
-__device__ __forceinline__ bool xw_ok(unsigned long long w, uint32_t need) { return (uint32_t)(w >> 32) == need; }
+constexpr uint32_t kXwAny = 0xffffffffu;        // timing experiments only (NB200_ABLATE & 16): accept any epoch
+__device__ __forceinline__ bool xw_ok(unsigned long long w, uint32_t need) { return (uint32_t)(w >> 32) == need || need == kXwAny; }
 __device__ __forceinline__ float xw_val(unsigned long long w) { return __uint_as_float((uint32_t)w); }
 // 4 consecutive words (32-byte aligned) -> float4 once all of them carry `need`
 static __device__ __noinline__ float4 xw_poll4_slow(const unsigned long long *p, uint32_t need, uint32_t *err) {
     unsigned long long a, b, c, d;
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (uint32_t it = 1;; it++) {
         xw_ld2(p, a, b); xw_ld2(p + 2, c, d);
         if (xw_ok(a, need) && xw_ok(b, need) && xw_ok(c, need) && xw_ok(d, need)) break;
-        if (clock64() - t0 > 4000000000ll) st_give_up(err, 0x50u);
+        if ((it & 255u) == 0) {                      // the clock is read rarely: the loop stays a pair of loads and four compares
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) st_give_up(err, 0x50u);
+        }
     }
     return make_float4(xw_val(a), xw_val(b), xw_val(c), xw_val(d));
 }
@@ -158,7 +166,7 @@ __device__ __forceinline__ void st_issue_kind(const StreamArgs &g, const StRing 
     for (uint32_t done = 0; done < rows; done += k.tile_rows) {
         const uint32_t tr = min(k.tile_rows, rows - done);
         const uint32_t bytes = (tr * (k.row_stride + k.aux_stride) + 15u) & ~15u;
-        mbar_wait(&r.empty[c.s], c.par, g.err, 0x10u);
+        mbar_wait(&r.empty[c.s], c.par, g.err, 0x10u, 200);
         r.tile_id[c.s] = issued++;
         mbar_expect_tx(&r.full[c.s], bytes);
         bulk_g2s(r.buf + (size_t)c.s * r.stage_bytes, src, bytes, &r.full[c.s]);
@@ -191,13 +199,15 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
                     const uint32_t tr = min(g.kv_tile_rows, t1 - t), bytes = tr * d.hd * 4u;
                     // The previous token's row was written with plain stores during this launch: it may be fetched once this
                     // CTA's consumers have passed that token's grid barrier (older rows: at least one barrier or launch ago).
-                    if (step > 0 && pos > 0 && pos - 1u >= t && pos - 1u < t + tr && *progress < step) {
-                        const long long c0 = clock64();
-                        while (*progress < step) { if (clock64() - c0 > 4000000000ll) st_give_up(g.err, 0x11u); }
+                    if (step > 0 && pos > 0 && pos - 1u >= t && pos - 1u < t + tr) {
+                        if (*progress < step) {
+                            const long long c0 = clock64();
+                            while (*progress < step) { __nanosleep(200); if (clock64() - c0 > 4000000000ll) st_give_up(g.err, 0x11u); }
+                        }
+                        asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores of this launch -> async-proxy (TMA) read
                     }
-                    mbar_wait(&r.empty[c.s], c.par, g.err, 0x12u);
+                    mbar_wait(&r.empty[c.s], c.par, g.err, 0x12u, 200);
                     r.tile_id[c.s] = issued++;
-                    asm volatile("fence.proxy.async.global;" ::: "memory");
                     mbar_expect_tx(&r.full[c.s], 2u * bytes);
                     unsigned char *dst = r.buf + (size_t)c.s * r.stage_bytes;
                     bulk_g2s(dst, kb + (size_t)t * d.hd, bytes, &r.full[c.s]);
@@ -220,7 +230,13 @@ static __device__ void st_producer(const StreamArgs &g, const StRing &r, const S
 //   Q4K (tensor.c:144-242): one 256-element block per warp, 8 elements per lane.
 // act layouts as in kernels.cuh (act_region_bytes).  KMAX warp slots per warp stay in registers between the
 // sum-of-squares pass and the quantise pass (host checks n <= st_prep_max_n).
+// fine-grained stamps inside a phase: compiled in only with -DNB200_FINE_TRACE (each costs ~200 cycles on the stamped path: a
+// divergent clock read + generic store in front of the next warp-synchronous instruction -- they distort what they measure)
+#ifdef NB200_FINE_TRACE
 #define ST_DBG(k) do { if (dbg && threadIdx.x == 0) dbg[k] = clock64(); } while (0)
+#else
+#define ST_DBG(k) do { } while (0)
+#endif
 template <int QUANT, int LPG>
 __device__ __forceinline__ void st_prep(const StreamArgs &g, const unsigned long long *xsrc, const float *ssrc, uint32_t need, const float *__restrict__ gain,
                                         uint32_t n, unsigned char *act, float *red, unsigned long long *dbg) {
@@ -286,95 +302,90 @@ __device__ __forceinline__ void st_prep(const StreamArgs &g, const unsigned long
             }
         }
     } else {
-        // Q80: a group (gs elements) is held by LG = gs/8 lanes, 8 elements (two float4) per lane, GW = 32/LG groups per warp slot.
-        // F32: no grouping semantics, 256-element slots.
-        constexpr uint32_t gs = (QUANT == 0x80) ? LPG * 16u : 256u;
-        constexpr uint32_t LG = gs / 8u;                                 // lanes per group (8, 16 or 32)
+        // Q80: a group (gs elements) is held by LG = gs/4 lanes, 4 elements (one float4) per lane, GW = 32/LG groups per warp slot
+        // (measured: one group per warp with 4 elements per lane has the shorter dependent chain; 8 per lane was ~600 cycles slower).
+        // F32: no grouping semantics, 128-element slots.
+        constexpr uint32_t gs = (QUANT == 0x80) ? LPG * 16u : 128u;
+        constexpr uint32_t LG = gs / 4u;                                 // lanes per group (16 or 32)
         constexpr uint32_t GW = 32u / LG;                                // groups per warp slot
-        static_assert(LG == 8 || LG == 16 || LG == 32, "stream kernel: Q80 group size 64 or 128");
+        static_assert(LG == 16 || LG == 32, "stream kernel: Q80 group size 64 or 128");
         const uint32_t G = (n + gs - 1u) / gs;                           // F32: n % 4 == 0 only, the last slot may be partial
         const uint32_t sub = lane / LG, li = lane % LG;
-        float4 v[kStKmax][2];
+        float4 v[kStKmax];
         if (ssrc) {
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
-#pragma unroll
-                for (int h = 0; h < 2; h++) v[j][h] = (i + 4u * h < n) ? *reinterpret_cast<const float4 *>(ssrc + i + 4 * h) : make_float4(0, 0, 0, 0);
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
+                v[j] = (i < n) ? *reinterpret_cast<const float4 *>(ssrc + i) : make_float4(0, 0, 0, 0);
             }
         } else {
             // every load of the thread is in flight before the first epoch is looked at
-            unsigned long long w[kStKmax][8];
+            unsigned long long w[kStKmax][4];
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
-#pragma unroll
-                for (int h = 0; h < 4; h++) if (i + 2u * h < n) xw_ld2(xsrc + i + 2 * h, w[j][2 * h], w[j][2 * h + 1]);
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
+                if (i < n) { xw_ld2(xsrc + i, w[j][0], w[j][1]); xw_ld2(xsrc + i + 2, w[j][2], w[j][3]); }
             }
 #pragma unroll
             for (int j = 0; j < kStKmax; j++) {
-                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 8u;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    v[j][h] = make_float4(0, 0, 0, 0);
-                    if (i + 4u * h < n) {
-                        const unsigned long long *ww = w[j] + 4 * h;
-                        if (xw_ok(ww[0], need) && xw_ok(ww[1], need) && xw_ok(ww[2], need) && xw_ok(ww[3], need))
-                            v[j][h] = make_float4(xw_val(ww[0]), xw_val(ww[1]), xw_val(ww[2]), xw_val(ww[3]));
-                        else v[j][h] = xw_poll4_slow(xsrc + i + 4 * h, need, g.err);
-                    }
+                const uint32_t i = ((warp + kConsWarps * j) * GW + sub) * gs + li * 4u;
+                v[j] = make_float4(0, 0, 0, 0);
+                if (i < n) {
+                    if (xw_ok(w[j][0], need) && xw_ok(w[j][1], need) && xw_ok(w[j][2], need) && xw_ok(w[j][3], need))
+                        v[j] = make_float4(xw_val(w[j][0]), xw_val(w[j][1]), xw_val(w[j][2]), xw_val(w[j][3]));
+                    else v[j] = xw_poll4_slow(xsrc + i, need, g.err);
                 }
             }
         }
         float ss = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kStKmax; j++) { ss = sq(v[j][0], ss); ss = sq(v[j][1], ss); }
+        for (int j = 0; j < kStKmax; j++) ss = sq(v[j], ss);
         ST_DBG(1);
         float inv = 1.0f;
-        if (gain) inv = inverse(ss);
+        if (gain && !(g.ablate & 8u)) inv = inverse(ss);
         ST_DBG(2);
 #pragma unroll
         for (int j = 0; j < kStKmax; j++) {
             const uint32_t g0 = (warp + kConsWarps * j) * GW;
             if (g0 < G) {                                            // warp-uniform
-                const uint32_t gi = g0 + sub, i = gi * gs + li * 8u;
-                float4 a0 = v[j][0], a1 = v[j][1];
-                const bool on0 = i < n, on1 = i + 4u < n;
-                if (gain) {
-                    if (on0) a0 = nrm(a0, __ldg(reinterpret_cast<const float4 *>(gain + i)), inv);
-                    if (on1) a1 = nrm(a1, __ldg(reinterpret_cast<const float4 *>(gain + i + 4)), inv);
-                }
+                const uint32_t gi = g0 + sub, i = gi * gs + li * 4u;
+                const bool on = i < n;
+                float4 a = v[j];
+                if (gain && on) a = nrm(a, __ldg(reinterpret_cast<const float4 *>(gain + i)), inv);
                 if constexpr (QUANT == 0x00) {
-                    if (on0) *reinterpret_cast<float4 *>(act + (size_t)i * 4u) = a0;
-                    if (on1) *reinterpret_cast<float4 *>(act + (size_t)i * 4u + 16u) = a1;
+                    if (on) *reinterpret_cast<float4 *>(act + (size_t)i * 4u) = a;
                 } else {
                     int8_t *codes = reinterpret_cast<int8_t *>(act);
                     float *scales = reinterpret_cast<float *>(act + ((n + 15u) & ~15u));
                     // tensor.c:21-46.  amax over the group with one REDUX (the values are non-negative: uint order == float order);
                     // the exact scale amax/127 is off the codes' critical path; codes come from q = v * (127/amax) rounded with the
                     // magic-number add, and any q within 1e-3 of a .5 boundary goes through the exact division + round().
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    float amax = 0.0f;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) amax = fmaxf(amax, fabsf(av[u]));
-                    const uint32_t gmask = (LG == 32u) ? 0xffffffffu : (((1u << LG) - 1u) << (LG * sub));
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+                    float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+                    const uint32_t gmask = (LG == 32u) ? 0xffffffffu : (0xffffu << (16u * sub));
                     amax = __uint_as_float(__reduce_max_sync(gmask, __float_as_uint(amax)));
                     const float sc = __fdiv_rn(amax, 127.0f);
                     const float rinv = __fdividef(127.0f, amax);
-                    if (on0) {
-                        uint32_t pk[2] = {0u, 0u};
-                        if (sc != 0.0f) {
+                    if (on) {
+                        uint32_t pk = 0;
+                        if (sc != 0.0f && !(g.ablate & 1u)) {
+                            int cq[4]; bool tie = false;
 #pragma unroll
-                            for (int u = 0; u < 8; u++) {
+                            for (int u = 0; u < 4; u++) {
                                 const float q = av[u] * rinv, aq = fabsf(q);
                                 const float rr = aq + 12582912.0f;                 // 1.5 * 2^23: the integer nearest to aq sits in the mantissa
                                 const float cf = rr - 12582912.0f;
-                                int c = __float_as_int(rr) - 0x4b400000;
-                                if (fabsf(aq - cf) > 0.499f) c = abs(q80_code_slow(av[u], sc));       // rare: within 1e-3 of a tie
-                                pk[u >> 2] |= ((uint32_t)(q < 0.0f ? -c : c) & 0xffu) << (8 * (u & 3));
+                                const int c = __float_as_int(rr) - 0x4b400000;
+                                tie = tie || fabsf(aq - cf) > 0.499f;
+                                cq[u] = q < 0.0f ? -c : c;
                             }
+                            if (tie) {                                           // rare: some q within 1e-3 of a tie -> the exact division + round()
+#pragma unroll
+                                for (int u = 0; u < 4; u++) cq[u] = q80_code_slow(av[u], sc);
+                            }
+                            pk = ((uint32_t)cq[0] & 0xffu) | (((uint32_t)cq[1] & 0xffu) << 8) | (((uint32_t)cq[2] & 0xffu) << 16) | (((uint32_t)cq[3] & 0xffu) << 24);
                         }
-                        *reinterpret_cast<uint2 *>(codes + i) = make_uint2(pk[0], pk[1]);
+                        *reinterpret_cast<uint32_t *>(codes + i) = pk;
                         if (li == 0) scales[gi] = sc;
                     }
                 }
@@ -428,43 +439,38 @@ __device__ __forceinline__ float st_row_q80_lpg(const unsigned char *wrow, const
     return val;
 }
 // Throughput form for warp-owned tiles: a whole warp owns RB rows, lanes split K in 16-byte chunks (512 bytes per step,
-// conflict-free), integer group sums via xor-shuffles inside the LPG lanes of a group, ordered fp32 combine via shuffles;
-// the row values end up in every lane.
+// conflict-free).  Nothing crosses lanes inside the loop: every lane keeps one fp32 partial per row
+// (exact integer sum of its 16 codes x the two group scales), the steps are independent of each other so the loads of
+// several steps are in flight at once, and one xor-butterfly per row at the end leaves the value in every lane.
+// (Fast mode: the fp32 summation order differs from matmul_quant infer.c:654-679; the bit-exact mode never runs this kernel.)
 template <int LPG, int RB>
 __device__ __forceinline__ void st_rows_q80_warp(const unsigned char *wrow, uint32_t row_stride, const unsigned char *srow, uint32_t aux_stride,
                                                  uint32_t n, const unsigned char *act, float (&val)[RB]) {
     constexpr uint32_t gs = LPG * 16;
-    constexpr int GPS = 32 / LPG;
     const int lane = threadIdx.x & 31;
     const float *xs = reinterpret_cast<const float *>(act + ((n + 15u) & ~15u));
+    float acc[RB];
 #pragma unroll
-    for (int r2 = 0; r2 < RB; r2++) val[r2] = 0.0f;
-    for (uint32_t k0 = 0; k0 < n; k0 += 512u) {
-        const uint32_t k = k0 + lane * 16u;
-        const bool on = k < n;
-        const uint32_t kc = on ? k : 0u;
-        const int4 xq = on ? *reinterpret_cast<const int4 *>(act + kc) : make_int4(0, 0, 0, 0);
-        const float xsc = xs[kc / gs];
-        float term[RB];
+    for (int r2 = 0; r2 < RB; r2++) acc[r2] = 0.0f;
+    auto step = [&](uint32_t k) {
+        const int4 xq = *reinterpret_cast<const int4 *>(act + k);
+        const uint32_t gi = k / gs;
+        const float xsc = xs[gi];
 #pragma unroll
         for (int r2 = 0; r2 < RB; r2++) {
-            const int4 w = *reinterpret_cast<const int4 *>(wrow + (size_t)r2 * row_stride + kc);
-            const float ws = reinterpret_cast<const float *>(srow + (size_t)r2 * aux_stride)[kc / gs];
-            int isum = __dp4a(w.x, xq.x, 0);
-            isum = __dp4a(w.y, xq.y, isum); isum = __dp4a(w.z, xq.z, isum); isum = __dp4a(w.w, xq.w, isum);
-#pragma unroll
-            for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
-            term[r2] = __fmul_rn(__fmul_rn((float)isum, ws), xsc);
+            const int4 w = *reinterpret_cast<const int4 *>(wrow + (size_t)r2 * row_stride + k);
+            const float ws = reinterpret_cast<const float *>(srow + (size_t)r2 * aux_stride)[gi];
+            const int s0 = __dp4a(w.y, xq.y, __dp4a(w.x, xq.x, 0)), s1 = __dp4a(w.w, xq.w, __dp4a(w.z, xq.z, 0));
+            acc[r2] = fmaf((float)(s0 + s1), ws * xsc, acc[r2]);
         }
+    };
+    uint32_t k = lane * 16u;
+    const uint32_t full = n & ~511u;
+#pragma unroll 2
+    for (; k < full; k += 512u) step(k);
+    if (k < n) step(k);
 #pragma unroll
-        for (int gq = 0; gq < GPS; gq++) {
-#pragma unroll
-            for (int r2 = 0; r2 < RB; r2++) {
-                const float t = __shfl_sync(0xffffffffu, term[r2], gq * LPG);
-                if (k0 + gq * gs < n) val[r2] = __fadd_rn(val[r2], t);
-            }
-        }
-    }
+    for (int r2 = 0; r2 < RB; r2++) val[r2] = warp_sum(acc[r2]);
 }
 // F32: matmul infer.c:637-651, fast mode (one warp per row: lane-split FMA + tree)
 __device__ __forceinline__ float st_row_f32(const unsigned char *wrow, uint32_t n, const unsigned char *act) {
@@ -514,17 +520,9 @@ __device__ __forceinline__ float st_row_q4k(const unsigned char *wrow, const uns
             term = __fsub_rn(term, __fmul_rn(__fmul_rn(q.x, bp), q.z));
             term = __fadd_rn(term, __fmul_rn(__fmul_rn(32.0f, bp), q.y));
         }
-        float dot = 0.0f;                       // per block: its 8 groups in order (lanes 8b..8b+7); then blocks in order
-        const int lead = lane & ~7;
-#pragma unroll
-        for (int g8 = 0; g8 < 8; g8++) dot = __fadd_rn(dot, __shfl_sync(0xffffffffu, term, lead + g8));
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const float t = __shfl_sync(0xffffffffu, dot, b * 8);
-            if (k0 + b * 128u < rowbytes) val = __fadd_rn(val, t);
-        }
+        val = __fadd_rn(val, term);             // lane-local partial (fast mode: the order of the fp32 sum differs from tensor.c:425-471)
     }
-    return val;
+    return warp_sum(val);
 }
 
 // ---------------------------------------------------------------- one matvec phase: tiles from the ring -> epilogue
@@ -580,29 +578,46 @@ __device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r,
                 const uint32_t tr = min(k.tile_rows, rows - done), want = tcount + j;
                 if (r.tile_id[cc.s] != want) {
                     const long long t0 = clock64();
-                    while (r.tile_id[cc.s] != want) { if (clock64() - t0 > 4000000000ll) st_give_up(g.err, 0x28u); }
+                    while (r.tile_id[cc.s] != want) { __nanosleep(20); if (clock64() - t0 > 4000000000ll) st_give_up(g.err, 0x28u); }
                 }
                 mbar_wait(&r.full[cc.s], cc.par, g.err, 0x29u);
                 const unsigned char *tile = r.buf + (size_t)cc.s * r.stage_bytes;
                 const unsigned char *aux = tile + (size_t)tr * k.row_stride;
-                for (uint32_t rr = 0; rr < tr; rr += 2u) {
-                    const bool two = rr + 1u < tr;
-                    const uint32_t r1 = two ? rr + 1u : rr;
-                    float v[2];
-                    if constexpr (QUANT == 0x80) {
-                        if (two) st_rows_q80_warp<LPG, 2>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v);
-                        else { float v1[1]; st_rows_q80_warp<LPG, 1>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v1); v[0] = v1[0]; v[1] = 0.0f; }
-                    } else if constexpr (QUANT == 0x42) {
-                        v[0] = st_row_q4k(tile + (size_t)rr * k.row_stride, aux + (size_t)rr * k.aux_stride, k.n, act);
-                        v[1] = two ? st_row_q4k(tile + (size_t)r1 * k.row_stride, aux + (size_t)r1 * k.aux_stride, k.n, act) : 0.0f;
-                    } else {
-                        v[0] = st_row_f32(tile + (size_t)rr * k.row_stride, k.n, act);
-                        v[1] = two ? st_row_f32(tile + (size_t)r1 * k.row_stride, k.n, act) : 0.0f;
+                // rows in blocks of 4 / 2 / 1 (SwiGLU tiles hold whole (w1, w3) pairs: an even row count)
+                auto out = [&](uint32_t rr, const float *v, uint32_t cnt) {
+                    if (epi == EPI_SWIGLU) { for (uint32_t u = 0; u + 1u < cnt; u += 2u) emit(row0 + done + rr + u, done + rr + u, v[u], v[u + 1u], true, (uint32_t)lane, 32u); }
+                    else { for (uint32_t u = 0; u < cnt; u++) emit(row0 + done + rr + u, done + rr + u, v[u], 0.0f, true, (uint32_t)lane, 32u); }
+                };
+                uint32_t rr = 0;
+                if constexpr (QUANT == 0x80) {
+                    for (; rr + 4u <= tr; rr += 4u) {
+                        float v[4];
+                        st_rows_q80_warp<LPG, 4>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v);
+                        out(rr, v, 4u);
                     }
-                    if (epi == EPI_SWIGLU) emit(row0 + done + rr, done + rr, v[0], v[1], true, (uint32_t)lane, 32u);
-                    else {
-                        emit(row0 + done + rr, done + rr, v[0], 0.0f, true, (uint32_t)lane, 32u);
-                        if (two) emit(row0 + done + r1, done + r1, v[1], 0.0f, true, (uint32_t)lane, 32u);
+                    if (rr + 2u <= tr) {
+                        float v[2];
+                        st_rows_q80_warp<LPG, 2>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v);
+                        out(rr, v, 2u); rr += 2u;
+                    }
+                    if (rr < tr) {
+                        float v[1];
+                        st_rows_q80_warp<LPG, 1>(tile + (size_t)rr * k.row_stride, k.row_stride, aux + (size_t)rr * k.aux_stride, k.aux_stride, k.n, act, v);
+                        out(rr, v, 1u);
+                    }
+                } else {
+                    for (; rr < tr; rr += 2u) {
+                        const bool two = rr + 1u < tr;
+                        const uint32_t r1 = two ? rr + 1u : rr;
+                        float v[2];
+                        if constexpr (QUANT == 0x42) {
+                            v[0] = st_row_q4k(tile + (size_t)rr * k.row_stride, aux + (size_t)rr * k.aux_stride, k.n, act);
+                            v[1] = two ? st_row_q4k(tile + (size_t)r1 * k.row_stride, aux + (size_t)r1 * k.aux_stride, k.n, act) : 0.0f;
+                        } else {
+                            v[0] = st_row_f32(tile + (size_t)rr * k.row_stride, k.n, act);
+                            v[1] = two ? st_row_f32(tile + (size_t)r1 * k.row_stride, k.n, act) : 0.0f;
+                        }
+                        out(rr, v, two ? 2u : 1u);
                     }
                 }
                 __syncwarp();
@@ -635,9 +650,9 @@ __device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r,
                     else if constexpr (QUANT == 0x42) return st_row_q4k(wrow, ax, k.n, act);
                     else return st_row_f32(wrow, k.n, act);
                 };
-                float v = one(rc), v3 = 0.0f;
+                float v = (g.ablate & 2u) ? 0.0f : one(rc), v3 = 0.0f;
                 bool pub = valid;                                                 // does this team publish the element?
-                if (mode == 2u) v3 = one(min(rc + 1u, tr - 1u));
+                if (mode == 2u && !(g.ablate & 2u)) v3 = one(min(rc + 1u, tr - 1u));
                 else if (mode == 1u) { v3 = __shfl_sync(0xffffffffu, v, (lane + TS) & 31u); pub = valid && !(team & 1u); }
                 ST_DBG(7);
                 emit(row0 + done + rc, done + rc, v, v3, pub, tl, TS);
@@ -663,10 +678,10 @@ __device__ __forceinline__ void st_consume(const StreamArgs &g, const StRing &r,
 // ---------------------------------------------------------------- attention item (infer.c:814-879) on K/V tiles from the ring
 // One CTA = one (kv head, split).  The item's rows are processed in segments of up to kStSegTiles ring tiles that are
 // resident at the same time; per segment three passes with no cross-lane traffic in their inner loops:
-//   scores : one thread per cache row, all KVM query heads of the kv head (K row and q read in 16-byte chunks whose order
+//   scores : four lanes per cache row, all KVM query heads of the kv head (K row and q read in 16-byte chunks whose order
 //            is rotated by the row index: conflict-free although rows are a multiple of 128 bytes apart)
 //   softmax: warp m owns query head m: running max / sum over the segments (online softmax), p = exp(s - max) in place
-//   P.V    : one thread per (head, output dim), rows in order
+//   P.V    : one thread per (head, pair of output dims), rows in order
 // q (and the position's k) are normalised + RoPE'd in registers (norm_rope_apply) by one warp each; the position's own K / V
 // rows (this step's QKV outputs) are written into their slots of the resident tile, so the passes treat all rows alike.
 // A range held by one item is normalised and published at once; otherwise every item publishes its partial and the item
@@ -677,7 +692,7 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
     const Dims &d = g.d;
     if (cta >= d.KV * nsplit) return;
     ST_DBG(0);
-    const uint32_t hd = d.hd, hd4 = hd / 4u;
+    const uint32_t hd = d.hd, hd4 = hd / 4u, hd2 = hd / 2u;
     const uint32_t kvh = cta / nsplit, sp = cta % nsplit;
     const uint32_t t0 = min(range, sp * chunk), t1 = min(range, t0 + chunk);
     const size_t kvl = (size_t)d.KV * d.max_seq * hd;
@@ -723,9 +738,9 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
             }
         }
     }
-    // running state: warp m < KVM keeps (max, sum) of head m; thread j (and j + 480) keeps the accumulator of (head, dim) j
+    // running state: warp m < KVM keeps (max, sum) of head m; thread j (and j + 480) keeps the accumulators of (head, dim pair) j
     float m_run = -FLT_MAX, l_run = 0.0f;
-    float acc[2] = {0.0f, 0.0f};
+    float2 acc[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
     cbar();
     ST_DBG(1);
 
@@ -754,42 +769,54 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
             cbar();
         }
         ST_DBG(3);
-        // ---- scores: task = (row, head, quarter of the dims); the 4 lanes of a task take interleaved 16-byte chunks (rotated by
-        //      the row index: conflict-free although rows are a multiple of 128 bytes apart) and combine with two shuffles ----
-        {
-            const uint32_t ntask = rows_seg * KVM;                 // (row, head) pairs; 4 lanes each
+        // ---- scores: task = (row, quarter of the dims), 4 adjacent lanes per row.  The K chunks of the row are loaded once and used for
+        //      all KVM query heads (q chunks are broadcast reads); chunk order rotated by the row index: conflict-free although rows are
+        //      a multiple of 128 bytes apart.  One round covers 120 rows. ----
+        if (!(g.ablate & 4u)) {
             const uint32_t part = threadIdx.x & 3u;
-            for (uint32_t t4 = threadIdx.x >> 2; t4 < ((ntask + 7u) & ~7u); t4 += kConsThreads / 4u) {       // warp-uniform trip count (8 tasks per warp)
-                const bool on = t4 < ntask;
-                const uint32_t tc = on ? t4 : 0u;
-                const uint32_t idx = tc / KVM, m = tc - idx * KVM;
-                const uint32_t ti = __umulhi(idx, g.kv_tile_magic), rr = idx - ti * kvr;
+            for (uint32_t idx = threadIdx.x >> 2; idx < ((rows_seg + 7u) & ~7u); idx += kConsThreads / 4u) {       // warp-uniform trip count (8 rows per warp)
+                const bool on = idx < rows_seg;
+                const uint32_t ic = on ? idx : 0u;
+                const uint32_t ti = __umulhi(ic, g.kv_tile_magic), rr = ic - ti * kvr;
                 const float *kr = tile_k(ti) + (size_t)rr * hd;
-                const float *qm = q_s + m * hd;
-                float a = 0.0f;
-                const uint32_t rot = (hd4 & 3u) ? 0u : 4u * (idx & 7u);       // rotation keeps the 4 lanes' chunk sets disjoint only if hd % 16 == 0
+                const uint32_t rot = (hd4 & 3u) ? 0u : (4u * (ic & 7u)) % hd4;       // rotation keeps the 4 lanes' chunk sets disjoint only if hd % 16 == 0
+                float a[KVM];
+#pragma unroll
+                for (int m = 0; m < KVM; m++) a[m] = 0.0f;
+#pragma unroll 4
                 for (uint32_t cc = part; cc < hd4; cc += 4u) {
-                    uint32_t ch = cc + rot; while (ch >= hd4) ch -= hd4;
-                    const float4 k4 = *reinterpret_cast<const float4 *>(kr + ch * 4u), q4 = *reinterpret_cast<const float4 *>(qm + ch * 4u);
-                    a = fmaf(k4.x, q4.x, fmaf(k4.y, q4.y, fmaf(k4.z, q4.z, fmaf(k4.w, q4.w, a))));
+                    uint32_t ch = cc + rot; if (ch >= hd4) ch -= hd4;
+                    const float4 k4 = *reinterpret_cast<const float4 *>(kr + ch * 4u);
+#pragma unroll
+                    for (int m = 0; m < KVM; m++) {
+                        const float4 q4 = *reinterpret_cast<const float4 *>(q_s + m * hd + ch * 4u);
+                        a[m] = fmaf(k4.x, q4.x, fmaf(k4.y, q4.y, fmaf(k4.z, q4.z, fmaf(k4.w, q4.w, a[m]))));
+                    }
                 }
-                a += __shfl_xor_sync(0xffffffffu, a, 1);
-                a += __shfl_xor_sync(0xffffffffu, a, 2);
-                if (on && part == 0) S[m * seg_max + idx] = __fdiv_rn(a, dv);         // infer.c:858
+#pragma unroll
+                for (int m = 0; m < KVM; m++) {
+                    a[m] += __shfl_xor_sync(0xffffffffu, a[m], 1);
+                    a[m] += __shfl_xor_sync(0xffffffffu, a[m], 2);
+                    if (on && part == 0) S[m * seg_max + idx] = __fdiv_rn(a[m], dv);         // infer.c:858
+                }
             }
         }
         cbar();
         ST_DBG(4);
         // ---- online softmax over the segment: warp m owns head m ----
-        if (warp < KVM) {
+        if (warp < KVM && !(g.ablate & 4u)) {
             float *Sm = S + warp * seg_max;
             float mx = -FLT_MAX;
             for (uint32_t i = lane; i < rows_seg; i += 32) mx = fmaxf(mx, Sm[i]);
+            ST_DBG(12);
             mx = warp_max(mx);
+            ST_DBG(13);
             const float mn = fmaxf(m_run, mx);
             const float sc_old = expf(m_run - mn);
+            ST_DBG(14);
             float ls = 0.0f;
             for (uint32_t i = lane; i < rows_seg; i += 32) { const float pr = expf(Sm[i] - mn); Sm[i] = pr; ls += pr; }
+            ST_DBG(15);
             ls = warp_sum(ls);
             l_run = fmaf(l_run, sc_old, ls);
             m_run = mn;
@@ -797,14 +824,15 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
         }
         cbar();
         ST_DBG(5);
-        // ---- P.V: thread j owns (head, dim) j; rows in order, four at a time (probabilities as one float4) ----
+        // ---- P.V: thread j owns (head, dim pair) j; rows in order, four at a time (probabilities as one float4) ----
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const uint32_t j = threadIdx.x + u * kConsThreads;
-            if (j < KVM * hd) {
-                const uint32_t m = j / hd, dd = j - m * hd;
+            if (j < KVM * hd2 && !(g.ablate & 4u)) {
+                const uint32_t m = j / hd2, dd = (j - m * hd2) * 2u;
                 const float *Sm = S + m * seg_max;
-                float a0 = acc[u] * st_scale[m], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                const float sc = st_scale[m];
+                float2 a0 = make_float2(acc[u].x * sc, acc[u].y * sc), a1 = make_float2(0, 0), a2 = a1, a3 = a1;
                 for (uint32_t ti = 0; ti < nt; ti++) {
                     const float *vt = tile_k(ti) + (size_t)kvr * hd + dd;
                     const uint32_t nr = min(kvr, rows_seg - ti * kvr);
@@ -812,12 +840,17 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
                     uint32_t rr = 0;
                     for (; rr + 4u <= nr; rr += 4u) {
                         const float4 p4 = *reinterpret_cast<const float4 *>(sp2 + rr);
-                        a0 = fmaf(p4.x, vt[(size_t)rr * hd], a0); a1 = fmaf(p4.y, vt[(size_t)(rr + 1u) * hd], a1);
-                        a2 = fmaf(p4.z, vt[(size_t)(rr + 2u) * hd], a2); a3 = fmaf(p4.w, vt[(size_t)(rr + 3u) * hd], a3);
+                        const float2 v0 = *reinterpret_cast<const float2 *>(vt + (size_t)rr * hd), v1 = *reinterpret_cast<const float2 *>(vt + (size_t)(rr + 1u) * hd);
+                        const float2 v2 = *reinterpret_cast<const float2 *>(vt + (size_t)(rr + 2u) * hd), v3 = *reinterpret_cast<const float2 *>(vt + (size_t)(rr + 3u) * hd);
+                        a0.x = fmaf(p4.x, v0.x, a0.x); a0.y = fmaf(p4.x, v0.y, a0.y); a1.x = fmaf(p4.y, v1.x, a1.x); a1.y = fmaf(p4.y, v1.y, a1.y);
+                        a2.x = fmaf(p4.z, v2.x, a2.x); a2.y = fmaf(p4.z, v2.y, a2.y); a3.x = fmaf(p4.w, v3.x, a3.x); a3.y = fmaf(p4.w, v3.y, a3.y);
                     }
-                    for (; rr < nr; rr++) a0 = fmaf(sp2[rr], vt[(size_t)rr * hd], a0);
+                    for (; rr < nr; rr++) {
+                        const float pr = sp2[rr]; const float2 v0 = *reinterpret_cast<const float2 *>(vt + (size_t)rr * hd);
+                        a0.x = fmaf(pr, v0.x, a0.x); a0.y = fmaf(pr, v0.y, a0.y);
+                    }
                 }
-                acc[u] = (a0 + a1) + (a2 + a3);
+                acc[u] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
             }
         }
         cbar();
@@ -832,16 +865,18 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         const uint32_t j = threadIdx.x + u * kConsThreads;
-        if (j < KVM * hd) { const uint32_t m = j / hd; outp[m * (hd + 2) + (j - m * hd)] = acc[u]; }
+        if (j < KVM * hd2) { const uint32_t m = j / hd2, dd = (j - m * hd2) * 2u; outp[m * (hd + 2) + dd] = acc[u].x; outp[m * (hd + 2) + dd + 1u] = acc[u].y; }
     }
     if (warp < KVM && lane == 0) { outp[warp * (hd + 2) + hd] = m_run; outp[warp * (hd + 2) + hd + 1] = l_run; }
     const uint32_t pw = KVM * (hd + 2);                               // words of one partial
     cbar();
     ST_DBG(8);
     if (nsplit == 1) {          // the whole range in one item: normalise and publish
-        for (uint32_t e = threadIdx.x; e < KVM * hd * (uint32_t)kStRep; e += kConsThreads) {
-            const uint32_t el = e / kStRep, rep = e % kStRep, m = el / hd, i = el % hd;
-            xw_st(g.xv[1] + (size_t)rep * g.rs[1] + ((size_t)kvh * KVM + m) * hd + i, __fdiv_rn(outp[m * (hd + 2) + i], outp[m * (hd + 2) + hd + 1]), e_out);
+        for (uint32_t el = threadIdx.x; el < KVM * hd; el += kConsThreads) {
+            const uint32_t m = el / hd, i = el - m * hd;
+            const float ov = __fdiv_rn(outp[m * (hd + 2) + i], outp[m * (hd + 2) + hd + 1]);
+#pragma unroll
+            for (uint32_t rep = 0; rep < (uint32_t)kStRep; rep++) xw_st(g.xv[1] + (size_t)rep * g.rs[1] + ((size_t)kvh * KVM + m) * hd + i, ov, e_out);
         }
         return;
     }
@@ -902,11 +937,13 @@ static __device__ void st_attention(const StreamArgs &g, const StRing &r, StCurs
         if (lane == 0) stat[warp] = L;
     }
     cbar();
-    for (uint32_t e = threadIdx.x; e < KVM * hd * (uint32_t)kStRep; e += kConsThreads) {
-        const uint32_t el = e / kStRep, rep = e % kStRep, m = el / hd, i = el % hd;
+    for (uint32_t el = threadIdx.x; el < KVM * hd; el += kConsThreads) {
+        const uint32_t m = el / hd, i = el - m * hd;
         float o = 0.0f;
         for (uint32_t s2 = 0; s2 < nsplit; s2++) o = fmaf(macc[(m * nsplit + s2) * hd + i], wsc[m * g.nsplit_max + s2], o);
-        xw_st(g.xv[1] + (size_t)rep * g.rs[1] + ((size_t)kvh * KVM + m) * hd + i, __fdiv_rn(o, stat[m]), e_out);
+        const float ov = __fdiv_rn(o, stat[m]);
+#pragma unroll
+        for (uint32_t rep = 0; rep < (uint32_t)kStRep; rep++) xw_st(g.xv[1] + (size_t)rep * g.rs[1] + ((size_t)kvh * KVM + m) * hd + i, ov, e_out);
     }
     ST_DBG(11);
 }
@@ -922,6 +959,7 @@ __device__ __forceinline__ void st_grid_barrier(const StreamArgs &g, unsigned in
             const long long t0 = clock64();
             while (ld_acquire_u32(g.bar) < target) { if (clock64() - t0 > 4000000000ll) st_give_up(g.err, 0x40u); }
         }
+        asm volatile("fence.proxy.async.global;" ::: "memory");      // the token's plain K/V stores are TMA-read by later tokens
         *progress = *progress + 1u;
     }
     cbar();
@@ -1000,7 +1038,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
         return;
     }
 
-    unsigned char *act = ssm + g.off_act;
+    unsigned char *act = ssm + g.off_act, *act_other = ssm + g.off_act2;
     float *x_s = reinterpret_cast<float *>(ssm + g.off_xs);
     float *attn_ws = reinterpret_cast<float *>(ssm + g.off_attn);
     const uint32_t rep = cta % (uint32_t)kStRep;                       // the replica this CTA reads
@@ -1042,11 +1080,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
                 else if (ph == SK_W13) { need = el + 3u; gain = g.g_ffn + (size_t)l * d.E; epi = EPI_SWIGLU; eout = el + 4u; }
                 else { xsrc = rhb; need = el + 4u; epi = EPI_RESID; eout = el + 5u; }
                 unsigned long long *dbg = (g.trace && cta == 0 && step + 1 == g.n_steps && l == d.L / 2) ? g.trace + 1100 + 16 * ph : nullptr;
+                if (g.ablate & 16u) need = kXwAny;
                 if (own.rows[kid]) {          // CTA-uniform: a CTA without rows of this kind neither reads the source nor publishes
+                    { unsigned char *t = act; act = act_other; act_other = t; }      // consecutive phases alternate between the two operands
                     st_prep<QUANT, LPG>(g, xsrc, ssrc, need, gain, k.n, act, ms.red, dbg);
                     ST_STAMP();
                     st_consume<QUANT, LPG>(g, ring, cur, tcount, k, epi, l, own.row0[kid], own.rows[kid], eout, act, pos, pen, xown, ms, geo, kid, dbg);
-                    cbar();        // the next phase (prologue or attention) overwrites the activation operand the slowest warp may still be reading
                 } else {
                     ST_STAMP();
                     if (cls && lane == 0) { ms.best_v[warp] = -FLT_MAX; ms.best_i[warp] = 0xffffffffu; }
@@ -1055,8 +1094,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_decode_stream(const __grid_cons
                 ST_TRACE();
                 if (cls) break;
                 if (ph == SK_QKV) {
-                    st_attention<KVM>(g, ring, cur, tcount, l, cta, pos, range, nsplit, chunk, el + 1u, el + 2u, attn_ws, dbg ? g.trace + 1100 + 64 : nullptr);
-                    cbar();                                              // the attention workspace aliases the activation operand
+                    st_attention<KVM>(g, ring, cur, tcount, l, cta, pos, range, nsplit, chunk, (g.ablate & 16u) ? kXwAny : el + 1u, el + 2u, attn_ws, dbg ? g.trace + 1100 + 64 : nullptr);
                     ST_STAMP();
                     ST_TRACE();
                 }

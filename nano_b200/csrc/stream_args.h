@@ -29,7 +29,7 @@ struct StreamArgs {
     const uint8_t *stream; uint64_t cta_stride, layer_stride, cls_off;
     StKind kind[5];
     uint32_t nstages, stage_bytes, kv_tile_rows, kv_tile_magic;      // magic = ceil(2^32 / kv_tile_rows): idx / kv_tile_rows == umulhi(idx, magic) for idx < 65536
-    uint32_t off_ring, off_act, off_xs, off_attn;     // byte offsets inside dynamic shared memory
+    uint32_t off_ring, off_act, off_act2, off_xs, off_attn;     // byte offsets inside dynamic shared memory (two activation operands: consecutive phases alternate)
     const float *g_attn, *g_ffn, *g_final;            // rmsnorm gains [L][E], [L][E], [E]
     const float *qnorm, *knorm, *rope_cos, *rope_sin;
     const void *emb_w, *emb_aux;
@@ -45,16 +45,18 @@ struct StreamArgs {
     unsigned int *bar;                                // grid barrier counter (zeroed by the host before every launch)
     uint32_t *err;                                    // set to a nonzero code before a spin gives up (and traps)
     uint32_t n_steps, nsplit_max, chunk_target;
+    uint32_t ablate;                                  // timing experiments only (NB200_ABLATE, results are wrong): 1 no quantise math, 2 no row dots, 4 no attention math,
+                                                      // 8 no sum of squares, 16 no waiting for epochs, 32 no publishing to replicas 1..7
     unsigned long long *trace;                        // optional: CTA 0 / thread 0 clock64() after every barrier of the LAST step
     Dims d;
 };
 
 // activation prologue: warp slots held in registers between the sum-of-squares pass and the quantise pass; the host
 // checks n <= st_prep_max_n before choosing the streaming kernel
-constexpr int kStKmax = 3, kStKmaxQ4K = 2;           // warp slots of 256 elements
+constexpr int kStKmax = 6, kStKmaxQ4K = 2;           // warp slots of 128 (Q80 / F32) or 256 (Q4K) elements
 __host__ __device__ inline uint32_t st_prep_max_n(uint32_t quant, uint32_t gs) {
     (void)gs;
-    return quant == 0x42u ? (uint32_t)kConsWarps * kStKmaxQ4K * 256u : (uint32_t)kConsWarps * kStKmax * 256u;
+    return quant == 0x42u ? (uint32_t)kConsWarps * kStKmaxQ4K * 256u : (uint32_t)kConsWarps * kStKmax * 128u;
 }
 
 // attention workspace of one CTA (floats): q [KVM][hd] | scores of a segment [KVM][seg rows] | per-head scale [KVM] |

@@ -49,7 +49,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = _build.ENGINE_SO
+        path = os.environ.get("NB200_ENGINE_SO", _build.ENGINE_SO)     # developer hook: the fine-trace build (tools/gpu_trace.py)
         if not os.path.exists(path):
             raise NB200Error(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                              "(nano_b200 has no CPU fallback)")
@@ -139,6 +139,9 @@ class Engine:
         self.vocab = self.vocab_size
         self.path = {4: "streaming kernel (persistent grid, per-CTA TMA ring over weights and KV, L2 grid barriers)",
                      1: "multi-kernel CUDA graph with PDL", 0: "multi-kernel direct launches"}[int(cfg.reserved[0])]
+        # creation-time calibration of the two fast paths (large one-GPU Q80 engines): us per token of each, None when not measured
+        self.calibration = ({"streaming_us_per_token": int(cfg.reserved[1]), "multikernel_us_per_token": int(cfg.reserved[2])}
+                            if int(cfg.reserved[1]) and int(cfg.reserved[2]) else None)
 
     # ---- LoRA plug-in ----
     def lora_load(self, image: bytes) -> None:

@@ -27,6 +27,16 @@ def test_baseline_shape_logits_and_ids(name, quant, gs):
     path = mf.cached_model(spec, quant, gs)
     S = 40
     eng = E.Engine(path, S)
+    if quant == mf.QUANT_Q80 and name == "qwen3-0.6b":
+        # a large one-GPU Q80 engine times both fast paths when it is created and keeps the faster one; the 40 positions below
+        # then also prove that the calibration steps (run at positions S/2..) left nothing behind
+        cal = eng.calibration
+        assert cal and cal["streaming_us_per_token"] > 0 and cal["multikernel_us_per_token"] > 0, cal
+        faster_is_stream = cal["streaming_us_per_token"] <= cal["multikernel_us_per_token"]
+        assert eng.path.startswith("streaming") == faster_is_stream, (eng.path, cal)
+        print("calibration:", cal)
+    else:
+        assert eng.calibration is None
     o = ob.NanoOracle(path, S)
     ob.NanoOracle.lib().nor_set_threads(min(32, os.cpu_count() or 1))
     toks = mf.teacher_tokens(S, spec.vocab)

@@ -30,5 +30,5 @@ for pos in (seq // 2, seq - 2):
         r = row - row[0]
         print(f"   inside {nm}: prep [loaded {r[1]}, inverse {r[2]}, quantised {r[3]}, cbar {r[4]}]  consume [enter {r[5]}, tile ready {r[6]}, (row: start {r[10]}, dp4a done {r[11]}, term {r[12]}, gathered {r[13]}) first row {r[7]}, tile done {r[8]}, out {r[9]}]"
               )
-    at = st_all[1100 + 64:1100 + 64 + 12]; at = at - at[0]
-    print(f"   inside attention (CTA 0 = kv head 0, split 0): q ready {at[1]}, tiles resident {at[2]}, k/v injected {at[3]}, scores {at[4]}, softmax {at[5]}, P.V {at[6]}, released {at[7]}, partial {at[8]}, (merge: start {at[9]}, partials polled {at[10]}, published {at[11]})")
+    at = st_all[1100 + 64:1100 + 64 + 16]; at = at - at[0]
+    print(f"   inside attention (CTA 0 = kv head 0, split 0): q ready {at[1]}, tiles resident {at[2]}, k/v injected {at[3]}, scores {at[4]}, softmax {at[5]}, P.V {at[6]}, released {at[7]}, partial {at[8]}, (merge: start {at[9]}, partials polled {at[10]}, published {at[11]}); softmax detail: max loop {at[12]}, warp_max {at[13]}, expf(old) {at[14]}, exp loop {at[15]}")
