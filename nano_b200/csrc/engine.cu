@@ -1461,7 +1461,7 @@ int nb200_op_q80_quantize(int8_t *codes, float *scales, const float *x, uint32_t
 int nb200_op_q80_matvec(float *out, const float *x, const int8_t *wc, const float *wscales, uint32_t n, uint32_t d, uint32_t gs) {
     if (!out || !x || !wc || !wscales || !n || !d) return fail(NB200_EINVAL, "bad argument");
     if ((gs != 32 && gs != 64 && gs != 128 && gs != 256) || n % gs) return fail(NB200_EINVAL, "unsupported group size");
-    return op_matvec(0x80u, out, x, wc, (size_t)d * n, wscales, (size_t)d * (n / gs) * 4, n, d, gs, 0, false);
+    return op_matvec(0x80u, out, x, wc, (size_t)d * n, wscales, (size_t)d * (n / gs) * 4, n, d, gs, 1, false);     // the operator is bit-exact: ordered group sum
 }
 
 int nb200_op_f32_matvec(float *out, const float *x, const float *w, uint32_t n, uint32_t d, uint32_t exact) {

@@ -9,11 +9,13 @@
 //
 // Numerics contract (DESIGN.md "Numerics"):
 //   * integer work (Q80 / Q4K group dots, activation codes) is exact;
-//   * every fp32 combine that follows an integer dot is evaluated in the reference's order with
-//     __fmul_rn/__fadd_rn (no FMA contraction), so a quantised matvec is bit-identical to the strict
-//     reference given the same activation vector;
-//   * the remaining fp32 reductions (rmsnorm sum, attention, F32 matvec) use parallel trees in fast
-//     mode and the reference's sequential order in exact mode.
+//   * exact mode (and the nb200_op_* operator entry points): every fp32 combine that follows an integer dot is
+//     evaluated in the reference's order with __fmul_rn/__fadd_rn (no FMA contraction), so a quantised matvec is
+//     bit-identical to the strict reference given the same activation vector; rmsnorm, attention and the F32 matvec
+//     use the reference's sequential order;
+//   * fast mode: the integer group dots are still exact, their fp32 terms are summed as one partial per lane plus a
+//     warp tree (Q80), and rmsnorm / attention / F32 matvec use parallel trees -- the deviation from the strict
+//     reference stays under the reference's own -ffast-math build noise (tests/golden/reference_noise_floor.json).
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -567,7 +569,10 @@ __device__ __forceinline__ void q80_load(Q80Tile<RB> &t, const int8_t *__restric
     }
 }
 
-template <int RB, int LPG>
+// ORD = true: the reference's left-to-right fp32 sum over groups, value replicated in every lane (exact mode, and the row-block
+// helpers below).  ORD = false (fast mode): every lane keeps one fp32 partial per row -- nothing crosses lanes inside the K loop --
+// and the caller finishes with one warp_sum per row.
+template <int RB, int LPG, bool ORD = true>
 __device__ __forceinline__ void q80_consume(const Q80Tile<RB> &t, uint32_t n, uint32_t k0, const unsigned char *act, float *val) {
     constexpr uint32_t gs = LPG * 16;
     constexpr int GPS = 32 / LPG;   // groups covered by one 512-byte step
@@ -588,6 +593,7 @@ __device__ __forceinline__ void q80_consume(const Q80Tile<RB> &t, uint32_t n, ui
             isum = __dp4a(t.w[s][r].y, xq.y, isum);
             isum = __dp4a(t.w[s][r].z, xq.z, isum);
             isum = __dp4a(t.w[s][r].w, xq.w, isum);
+            if (!ORD) { val[r] = fmaf((float)isum, t.ws[s][r] * xsc, val[r]); continue; }
 #pragma unroll
             for (int o = 1; o < LPG; o <<= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
             const float term = __fmul_rn(__fmul_rn((float)isum, t.ws[s][r]), xsc);
@@ -817,16 +823,25 @@ __device__ __forceinline__ void matvec_phase(const MatvecArgs &a, uint32_t cta, 
                 else if (dd == 0 || dd * 1024u < a.n)
                     q80_load<RB, LPG>(t[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, dd * 1024u);
             }
-            for (uint32_t k0 = 0; k0 < a.n; k0 += D * 1024u) {
+            auto kloop = [&](auto ord_tag) {
+                constexpr bool kOrd = decltype(ord_tag)::value;
+                for (uint32_t k0 = 0; k0 < a.n; k0 += D * 1024u) {
 #pragma unroll
-                for (int dd = 0; dd < D; dd++) {
-                    const uint32_t k = k0 + dd * 1024u;
-                    if (dd == 0 || k < a.n) {
-                        q80_consume<RB, LPG>(t[dd], a.n, k, act, val);       // K ascending: the reference's group order
-                        if (k + D * 1024u < a.n)
-                            q80_load<RB, LPG>(t[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, k + D * 1024u);
+                    for (int dd = 0; dd < D; dd++) {
+                        const uint32_t k = k0 + dd * 1024u;
+                        if (dd == 0 || k < a.n) {
+                            q80_consume<RB, LPG, kOrd>(t[dd], a.n, k, act, val);       // K ascending: the reference's group order
+                            if (k + D * 1024u < a.n)
+                                q80_load<RB, LPG>(t[dd], static_cast<const int8_t *>(a.w), static_cast<const float *>(a.w_aux), row0, a.rows, a.n, k + D * 1024u);
+                        }
                     }
                 }
+            };
+            if (exact) kloop(std::true_type{});
+            else {
+                kloop(std::false_type{});
+#pragma unroll
+                for (int r = 0; r < RB; r++) val[r] = warp_sum(val[r]);
             }
         } else rows_q4k<RB>(static_cast<const uint8_t *>(a.w), static_cast<const uint8_t *>(a.w_aux), row0, a.rows, a.n, act, val);
 
@@ -1260,7 +1275,7 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sub = lane / lpr, li = lane % lpr, col = li * 4;
     const bool colon = col < hd;
-    const float inv_dv = 1.0f / sqrtf((float)hd);   // fast mode: score * (1/sqrt(hd)) and __expf; exact mode has its own kernel
+    const float dv = sqrtf((float)hd);              // infer.c:858 divides by sqrt(head_dim); expf as the reference (the sums stay parallel in fast mode)
 
     // Everything that does not depend on other loads is requested first: q, the position's RoPE entries, the head-norm
     // gain, and the warp's first batch of cache rows.  (One memory round trip instead of three or four in sequence.)
@@ -1326,7 +1341,7 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
                 float sdot = kr[u].x * qv[m].x;
                 sdot = fmaf(kr[u].y, qv[m].y, sdot); sdot = fmaf(kr[u].z, qv[m].z, sdot); sdot = fmaf(kr[u].w, qv[m].w, sdot);
                 for (uint32_t o = lpr >> 1; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
-                scr[u][m] = vld[u] ? sdot * inv_dv : -FLT_MAX;
+                scr[u][m] = vld[u] ? __fdiv_rn(sdot, dv) : -FLT_MAX;
             }
         }
 #pragma unroll
@@ -1335,12 +1350,12 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
 #pragma unroll
             for (int u = 1; u < U; u++) bm = fmaxf(bm, scr[u][m]);
             const float mn = fmaxf(mx[m], bm);
-            const float a = __expf(mx[m] - mn);
+            const float a = expf(mx[m] - mn);
             float l2 = ls[m] * a;
             float4 a4 = make_float4(av[m].x * a, av[m].y * a, av[m].z * a, av[m].w * a);
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const float pr = vld[u] ? __expf(scr[u][m] - mn) : 0.0f;
+                const float pr = vld[u] ? expf(scr[u][m] - mn) : 0.0f;
                 l2 += pr;
                 a4.x = fmaf(pr, vr[u].x, a4.x); a4.y = fmaf(pr, vr[u].y, a4.y); a4.z = fmaf(pr, vr[u].z, a4.z); a4.w = fmaf(pr, vr[u].w, a4.w);
             }
@@ -1358,7 +1373,7 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
             float4 ao;
             ao.x = __shfl_xor_sync(0xffffffffu, av[m].x, off); ao.y = __shfl_xor_sync(0xffffffffu, av[m].y, off);
             ao.z = __shfl_xor_sync(0xffffffffu, av[m].z, off); ao.w = __shfl_xor_sync(0xffffffffu, av[m].w, off);
-            const float mn = fmaxf(mx[m], mo), a = __expf(mx[m] - mn), bsc = __expf(mo - mn);
+            const float mn = fmaxf(mx[m], mo), a = expf(mx[m] - mn), bsc = expf(mo - mn);
             ls[m] = ls[m] * a + lo * bsc;
             av[m].x = av[m].x * a + ao.x * bsc; av[m].y = av[m].y * a + ao.y * bsc;
             av[m].z = av[m].z * a + ao.z * bsc; av[m].w = av[m].w * a + ao.w * bsc;
@@ -1382,7 +1397,7 @@ __device__ __forceinline__ void attn_stream_partial(const Dims &d, const float *
         float M = -FLT_MAX;
         for (int w = 0; w < NW; w++) M = fmaxf(M, ws[((size_t)w * KVM + m) * (hd + 4) + hd]);
         float *wp = ws + (size_t)threadIdx.x * (hd + 4);          // threadIdx.x == w * KVM + m
-        wp[hd + 2] = __expf(wp[hd] - M);
+        wp[hd + 2] = expf(wp[hd] - M);
         wp[hd + 3] = M;
     }
     __syncthreads();
