@@ -21,9 +21,10 @@
 // One true grid barrier per token (release/acquire, at the classifier) orders the plain stores -- KV-cache rows, logits,
 // ids, repetition-penalty flags -- against the next token's reads (TMA reads of the cache included).
 //
-// Arithmetic is the same as the multi-kernel path (kernels.cuh): exact integer group dots, the reference's fp32 order
-// for the combine of a quantised row (infer.c:668-674, tensor.c:425-430), tree reductions for rmsnorm / attention
-// (fast mode).  Reference: llm_forward infer/infer.c:971-1018, transformer_block_forward :713-966.
+// Arithmetic (fast mode only; the bit-exact mode never runs this kernel): exact integer group dots; the fp32 combine of a
+// quantised row (infer.c:668-674, tensor.c:425-430) in the reference's order on shared tiles and as one partial per lane
+// + a warp tree on warp-owned tiles; tree reductions for rmsnorm / attention, expf and the division by sqrt(head_dim) as
+// the reference.  Reference: llm_forward infer/infer.c:971-1018, transformer_block_forward :713-966.
 #pragma once
 #include "kernels.cuh"
 #include "stream_args.h"

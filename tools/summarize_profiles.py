@@ -96,3 +96,84 @@ def round_outputs(src_dir, tag="r1"):
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "round":
     round_outputs(sys.argv[2])
+
+
+# ---------------------------------------------------------------- round 2
+def full_report_wide(rep, out_md, title, note=""):
+    """One row per captured launch with the metrics that explain a persistent kernel: time, DRAM bytes, issue utilisation, stall reasons."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
+    hdr, units = r[0], r[1]
+    want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum", "dram__bytes_read.sum",
+            "dram__bytes_write.sum", "dram__bytes_read.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "smsp__inst_executed.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+    stalls = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
+    idx = [hdr.index(w) for w in want if w in hdr]
+    with open(out_md, "w") as f:
+        f.write(f"# {title}\n\nSource: `{os.path.relpath(rep, ROOT)}` (`ncu --set full --clock-control none --import-source on`), one block per captured launch."
+                f"  Numbers taken under the profiler are never bench values.\n\n{note}\n")
+        for row in r[2:]:
+            f.write(f"\n## `{row[hdr.index('Kernel Name')][:100]}`\n\n| metric | value |\n|---|---|\n")
+            for i in idx[1:]:
+                f.write(f"| {hdr[i]} ({units[i]}) | {row[i][:40]} |\n")
+            st = sorted(((float(row[hdr.index(h)]), h) for h in stalls), reverse=True)
+            f.write("| warp stall reasons per issued instruction (top 6) | " + ", ".join(
+                f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.2f}" for v, h in st[:6]) + " |\n")
+    return r
+
+
+def round2(src="r2final"):
+    g = os.path.join(ROOT, "gpurun_out", src); p = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(g)):
+        if f.startswith("bench_") and f.endswith(".json") and os.path.getsize(os.path.join(g, f)) > 10:
+            open(os.path.join(p, "r2_" + f), "w").write(open(os.path.join(g, f)).read())
+        if f.startswith("micro_") or f in ("pytest_gpu.log", "smoke.log"):
+            open(os.path.join(p, "r2_" + f), "w").write(open(os.path.join(g, f)).read())
+    if os.path.exists(os.path.join(g, "launches_default_n168.csv")):
+        launch_list(os.path.join(g, "launches_default_n168.csv"), os.path.join(p, "r2_launches_default.md"),
+                    "Round 2 - launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra` (Nano-168M Q80 seq 512: the streaming kernel is the step)")
+    traffic = {}
+    rep = os.path.join(g, "prof_stream_n168.ncu-rep")
+    if os.path.exists(rep):
+        r = full_report_wide(rep, os.path.join(p, "r2_ncu_stream.md"), "Round 2 - ncu --set full, streaming kernel k_decode_stream (Nano-168M Q80)",
+                             "The captured launch decodes 32 tokens (positions 15..46 of a seq-512 engine): divide time and bytes by 32 for per-token figures.")
+        hdr = r[0]; row = r[2]
+        rd = float(row[hdr.index("dram__bytes_read.sum")]); wr = float(row[hdr.index("dram__bytes_write.sum")])
+        mul = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+        rd *= mul[r[1][hdr.index("dram__bytes_read.sum")]]; wr *= mul[r[1][hdr.index("dram__bytes_write.sum")]]
+        traffic["nano-168m-q80:stream"] = (rd + wr) / 32.0
+    rep = os.path.join(g, "prof_multikernel_q06.ncu-rep")
+    if os.path.exists(rep):
+        r = full_report_wide(rep, os.path.join(p, "r2_ncu_multikernel.md"), "Round 2 - ncu --set full, multi-kernel path (Qwen3-0.6B Q80, ten consecutive kernels around position 1000)")
+        hdr = r[0]
+        mul = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
+        best = 0.0
+        for row in r[2:]:      # the W1|W3 kernel is the one with the most DRAM bytes among the layer's kernels
+            b = float(row[hdr.index("dram__bytes_read.sum")]) * mul[r[1][hdr.index("dram__bytes_read.sum")]] + float(row[hdr.index("dram__bytes_write.sum")]) * mul[r[1][hdr.index("dram__bytes_write.sum")]]
+            best = max(best, b)
+        if best: traffic["qwen3-0.6b-q80:multikernel"] = best
+    if traffic:
+        json.dump(traffic, open(os.path.join(p, "r2_traffic.json"), "w"), indent=1)
+    # table of every committed round-2 bench line
+    rows = []
+    for f in sorted(os.listdir(p)):
+        if not (f.startswith("r2_bench_") and f.endswith(".json")): continue
+        try: d = json.loads(open(os.path.join(p, f)).read().strip().splitlines()[-1])
+        except Exception: continue
+        run = d.get("run") or {}; tr = d.get("token_roofline") or {}; e2e = d.get("e2e") or {}
+        rows.append((f, d.get("impl", "b200"), d["config"]["workload"].split(",")[0], d.get("n_gpus"), d.get("value"), e2e.get("value"), run.get("engine", "")[:28],
+                     tr.get("frac_of_peak"), (d.get("cpu_baseline") or {}).get("value")))
+        for w, x in (d.get("configs") or {}).items():
+            rows.append((f + " (configs)", "b200", w, d.get("n_gpus"), x.get("value"), (x.get("e2e") or {}).get("value"), x.get("engine", "")[:28], None, None))
+        if d.get("exact_mode"):
+            rows.append((f + " (exact_mode)", "b200", d["config"]["workload"].split(",")[0], d.get("n_gpus"), d["exact_mode"].get("value"), None, d["exact_mode"].get("engine", "")[:28], None, None))
+    with open(os.path.join(p, "r2_paths.md"), "w") as f:
+        f.write("# Round 2 - every committed bench line (tokens/s, decode segment)\n\n| file | arm | workload | GPUs | value | e2e | engine | fraction of HBM peak (token roofline) | cpu_baseline |\n|---|---|---|---|---|---|---|---|---|\n")
+        fmt = lambda v: "" if v is None else (f"{v:.1f}" if isinstance(v, float) and v > 2 else f"{v:.3f}" if isinstance(v, float) else str(v))
+        for r_ in rows:
+            f.write("| " + " | ".join(fmt(v) for v in r_) + " |\n")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "round2":
+    round2(sys.argv[2] if len(sys.argv) > 2 else "r2final")
