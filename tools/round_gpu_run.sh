@@ -30,8 +30,9 @@ NB200_STREAM=0 b bench_q06_q4k_multikernel --workload qwen3-0.6b-q4k --steps 2
 for m in lat_bench bar_bench exchange_bench ring_bench consume_bench; do
   [ -x tools/micro/$m ] && (timeout 120 tools/micro/$m > $out/micro_$m.log 2>&1; tail -3 $out/micro_$m.log)
 done
-# launch list of the default command (never a bench value), then full captures
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_default_n168.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra > $out/under_ncu_default.log 2>&1
+# launch list of the default command restricted to the step's kernel (never a bench value).  Keep -k / -c: an unrestricted list of
+# this command profiles every kernel of the per-kernel orientation pass one by one and takes half an hour.
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_decode_stream -c 6 --csv --log-file $out/launches_default_n168.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra > $out/under_ncu_default.log 2>&1
 cat > /tmp/cap.py <<'PY'
 import os, sys
 import numpy as np
@@ -44,8 +45,9 @@ ids = np.zeros(seq + 1, np.uint32); ids[:16] = [17 + i % 10 for i in range(16)] 
 eng.decode_greedy(ids, 16, n_total)
 print(eng.path)
 PY
-# streaming kernel: launch 0 = 15 prompt positions, launch 1 = 32 decode positions (captured)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_decode_stream -s 1 -c 1 -o $out/prof_stream_n168 -f python /tmp/cap.py nano-168m q80 512 48 > $out/ncu_stream.log 2>&1
-# multi-kernel path (Qwen3-0.6B Q80): ten consecutive kernels (two layers) around position 1000 (141 matching launches per token)
-NB200_STREAM=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_matvec|k_attention' -s 141300 -c 10 -o $out/prof_multikernel_q06 -f python /tmp/cap.py qwen3-0.6b q80 2048 1030 > $out/ncu_multi.log 2>&1
+# streaming kernel: launch 0 = 15 prompt positions, launch 1 = 32 decode positions (captured; ~1 minute)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_decode_stream -s 1 -c 1 -o $out/prof_stream_n168 -f python /tmp/cap.py nano-168m q80 512 48 > $out/ncu_stream.log 2>&1
+# multi-kernel path (Qwen3-0.6B Q80): the kernels of one layer early in the decode segment (141 matching launches per token; a large
+# --launch-skip is slow under ncu, and a report of more than ~6 kernels exceeds what gpurun copies back together with the one above)
+NB200_STREAM=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_matvec|k_attention' -s 2400 -c 5 -o $out/prof_multikernel_q06 -f python /tmp/cap.py qwen3-0.6b q80 2048 40 > $out/ncu_multi.log 2>&1
 ls -la $out | tail -40

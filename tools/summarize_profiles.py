@@ -145,7 +145,7 @@ def round2(src="r2final"):
         traffic["nano-168m-q80:stream"] = (rd + wr) / 32.0
     rep = os.path.join(g, "prof_multikernel_q06.ncu-rep")
     if os.path.exists(rep):
-        r = full_report_wide(rep, os.path.join(p, "r2_ncu_multikernel.md"), "Round 2 - ncu --set full, multi-kernel path (Qwen3-0.6B Q80, ten consecutive kernels around position 1000)")
+        r = full_report_wide(rep, os.path.join(p, "r2_ncu_multikernel.md"), "Round 2 - ncu --set full, multi-kernel path (Qwen3-0.6B Q80, the kernels of one layer early in the decode segment)")
         hdr = r[0]
         mul = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
         best = 0.0
