@@ -298,6 +298,75 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
     return {"path": path, "bytes": size, "spec": spec, "quant": quant, "gs": gs}
 
 
+def write_model_from_weights(path: str, spec: ModelSpec, quant: int, gs: int, weights: Dict[str, np.ndarray],
+                             tokenizer_section: Optional[bytes] = None, rope_tables: bool = True) -> dict:
+    """Write a model file from GIVEN float32 weights (the export path: tools/export_qwen.py:442-636 for arch 3, export.py:228-475 for
+    arch 0) in the same section order as `write_model`.  `weights`: attn_norm [L,E], ffn_norm [L,E], final_norm [E], emb [V,E],
+    wq [L,Q,E], wk [L,K,E], wv [L,K,E], wo [L,E,Q], w1 [L,F,E], w2 [L,E,F], w3 [L,F,E]; arch 3 also q_norm [L,hd], k_norm [L,hd];
+    an untied model also cls [V,E] (Q80 files only, infer.c:206-216).  `rope_tables`: arch 3 files of the reference exporter carry a
+    (cos, sin) table the engine never reads (infer.c:189-204 rebuilds it); written by default so that the untied classifier, which
+    the loader looks for behind a table-sized gap (infer.c:201-202), lands where the reference expects it."""
+    L, E, F, V = spec.n_layer, spec.n_embd, spec.n_hidden, spec.vocab
+    Q, K, hd = spec.q_dim, spec.kv_dim, spec.hd
+    shapes = {"attn_norm": (L, E), "ffn_norm": (L, E), "final_norm": (E,), "emb": (V, E), "wq": (L, Q, E), "wk": (L, K, E), "wv": (L, K, E),
+              "wo": (L, E, Q), "w1": (L, F, E), "w2": (L, E, F), "w3": (L, F, E)}
+    if spec.arch == ARCH_QWEN3:
+        shapes.update({"q_norm": (L, hd), "k_norm": (L, hd)})
+    if not spec.tied:
+        shapes["cls"] = (V, E)
+    w = {}
+    for k, shp in shapes.items():
+        a = np.ascontiguousarray(weights[k], dtype=np.float32)
+        assert a.shape == shp, f"{k}: shape {a.shape}, expected {shp}"
+        w[k] = a
+    if quant == QUANT_Q80:
+        assert E % gs == 0 and Q % gs == 0 and F % gs == 0, "group size must divide E, q_dim and F"
+    if quant == QUANT_Q4K:
+        assert E % 256 == 0 and Q % 256 == 0 and F % 256 == 0 and spec.tied, "Q4K needs n % 256 == 0 and a tied classifier"
+    assert spec.tied or quant == QUANT_Q80, "untied classifier: Q80 files only"
+    assert spec.arch != ARCH_QWEN2, "Qwen2 export (biases) is not provided"
+
+    hdr = np.zeros(64, dtype=np.uint32)
+    hdr[0], hdr[1] = 0x42443453, 0x55524C4D
+    hdr[2], hdr[3] = 2025, 12
+    hdr[4] = spec.arch
+    hdr[6:15] = [spec.block_size, V, L, E, spec.n_head, spec.n_kv_head, F, spec.tied, spec.head_dim]
+    hdr[15], hdr[16] = quant, gs if quant == QUANT_Q80 else 0
+
+    def emit(f, a2d):
+        if quant == QUANT_F32:
+            f.write(a2d.tobytes())
+        elif quant == QUANT_Q80:
+            q, s = quantize_q80(a2d, gs)
+            f.write(q.tobytes()); f.write(s.tobytes())
+        else:
+            f.write(quantize_q4k_blocks(a2d).tobytes())
+
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        f.write(tokenizer_section if tokenizer_section is not None else
+                (_nano_tokenizer_section(V) if spec.arch == ARCH_NANO else _qwen_tokenizer_section(V)))
+        f.write(w["attn_norm"].tobytes()); f.write(w["ffn_norm"].tobytes()); f.write(w["final_norm"].tobytes())
+        if quant == QUANT_Q4K:
+            f.write(q4k_frame((V, E), V * (E // 256)))
+        emit(f, w["emb"])
+        for name, d, n in (("wq", Q, E), ("wk", K, E), ("wv", K, E), ("wo", E, Q), ("w1", F, E), ("w2", E, F), ("w3", F, E)):
+            if quant == QUANT_Q4K:
+                f.write(q4k_frame((L, d, n), L * d * (n // 256)))
+            for l in range(L):
+                emit(f, w[name][l])
+        if spec.arch == ARCH_QWEN3:
+            f.write(w["q_norm"].tobytes()); f.write(w["k_norm"].tobytes())
+        if spec.arch == ARCH_NANO or (rope_tables and quant != QUANT_Q4K) or not spec.tied:
+            c, sn = _rope_table(spec.block_size, hd, 1000000.0 if spec.arch == ARCH_QWEN3 else 10000.0)
+            f.write(c.tobytes()); f.write(sn.tobytes())
+        if not spec.tied:
+            q, s = quantize_q80(w["cls"], gs)
+            f.write(q.tobytes()); f.write(s.tobytes())
+        size = f.tell()
+    return {"path": path, "bytes": size, "spec": spec, "quant": quant, "gs": gs}
+
+
 def write_lora(spec: ModelSpec, rank: int = 8, alpha: int = 16, seed: int = 7, std: float = 0.05) -> bytes:
     """A synthetic LoRA plug-in image in the reference's layout (infer.c:436-500): 256-byte header
     {magic0, magic1, major, minor, model_type, config_length, rank, alpha, n_layer, n_embd, n_head, n_kv_head, n_hidden,
