@@ -180,6 +180,16 @@ def _nano_tokenizer_section(vocab: int) -> bytes:
     return struct.pack("<II", 8 + len(body), vocab) + body
 
 
+def nano_tokenizer_section_from_config(tokenizer_config: dict) -> bytes:
+    """The Nano tokenizer section of a real export (export.py:72-113): `itos` (list of token strings), `special_tokens`."""
+    vocab, special = tokenizer_config["itos"], set(tokenizer_config.get("special_tokens", []))
+    parts = []
+    for i, t in enumerate(vocab):
+        parts.append(struct.pack("<BBBBI", len(t), 1 if t in special else 0, 255, 255, i) + struct.pack("<%dI" % len(t), *[ord(c) for c in t]))
+    body = b"".join(parts)
+    return struct.pack("<II", 8 + len(body), int(tokenizer_config["vocab_size"])) + body
+
+
 def _qwen_tokenizer_section(vocab: int) -> bytes:
     n = max(vocab, QWEN_TOKENIZER_ENTRIES)
     parts = []
@@ -299,13 +309,16 @@ def write_model(path: str, spec: ModelSpec, quant: int, gs: int = 128, seed: int
 
 
 def write_model_from_weights(path: str, spec: ModelSpec, quant: int, gs: int, weights: Dict[str, np.ndarray],
-                             tokenizer_section: Optional[bytes] = None, rope_tables: bool = True) -> dict:
+                             tokenizer_section: Optional[bytes] = None, rope_tables: bool = True, version=(2026, 1),
+                             rope: Optional[tuple] = None) -> dict:
     """Write a model file from GIVEN float32 weights (the export path: tools/export_qwen.py:442-636 for arch 3, export.py:228-475 for
     arch 0) in the same section order as `write_model`.  `weights`: attn_norm [L,E], ffn_norm [L,E], final_norm [E], emb [V,E],
     wq [L,Q,E], wk [L,K,E], wv [L,K,E], wo [L,E,Q], w1 [L,F,E], w2 [L,E,F], w3 [L,F,E]; arch 3 also q_norm [L,hd], k_norm [L,hd];
     an untied model also cls [V,E] (Q80 files only, infer.c:206-216).  `rope_tables`: arch 3 files of the reference exporter carry a
     (cos, sin) table the engine never reads (infer.c:189-204 rebuilds it); written by default so that the untied classifier, which
-    the loader looks for behind a table-sized gap (infer.c:201-202), lands where the reference expects it."""
+    the loader looks for behind a table-sized gap (infer.c:201-202), lands where the reference expects it.  `rope`: the (cos, sin)
+    tables to write, [block_size, hd/2] each -- an exporter passes the checkpoint's own buffers (arch 0 engines READ this table,
+    infer.c:181-187, and torch's pow / cos differ from NumPy's by an ulp here and there); default: `_rope_table`."""
     L, E, F, V = spec.n_layer, spec.n_embd, spec.n_hidden, spec.vocab
     Q, K, hd = spec.q_dim, spec.kv_dim, spec.hd
     shapes = {"attn_norm": (L, E), "ffn_norm": (L, E), "final_norm": (E,), "emb": (V, E), "wq": (L, Q, E), "wk": (L, K, E), "wv": (L, K, E),
@@ -328,9 +341,9 @@ def write_model_from_weights(path: str, spec: ModelSpec, quant: int, gs: int, we
 
     hdr = np.zeros(64, dtype=np.uint32)
     hdr[0], hdr[1] = 0x42443453, 0x55524C4D
-    hdr[2], hdr[3] = 2025, 12
-    hdr[4] = spec.arch
-    hdr[6:15] = [spec.block_size, V, L, E, spec.n_head, spec.n_kv_head, F, spec.tied, spec.head_dim]
+    hdr[2], hdr[3] = version                     # the current exporters write 2026 / 1 (export.py:240-241); the engine does not look at it
+    hdr[4], hdr[5] = spec.arch, 36               # model type, config length (export.py:255-256)
+    hdr[6:15] = [spec.block_size, V, L, E, spec.n_head, spec.n_kv_head, F, spec.tied, spec.head_dim if spec.arch == ARCH_QWEN3 else spec.hd]
     hdr[15], hdr[16] = quant, gs if quant == QUANT_Q80 else 0
 
     def emit(f, a2d):
@@ -358,7 +371,9 @@ def write_model_from_weights(path: str, spec: ModelSpec, quant: int, gs: int, we
         if spec.arch == ARCH_QWEN3:
             f.write(w["q_norm"].tobytes()); f.write(w["k_norm"].tobytes())
         if spec.arch == ARCH_NANO or (rope_tables and quant != QUANT_Q4K) or not spec.tied:
-            c, sn = _rope_table(spec.block_size, hd, 1000000.0 if spec.arch == ARCH_QWEN3 else 10000.0)
+            c, sn = rope if rope is not None else _rope_table(spec.block_size, hd, 1000000.0 if spec.arch == ARCH_QWEN3 else 10000.0)
+            c, sn = np.ascontiguousarray(c, np.float32), np.ascontiguousarray(sn, np.float32)
+            assert c.shape == sn.shape == (spec.block_size, hd // 2), (c.shape, spec.block_size, hd)
             f.write(c.tobytes()); f.write(sn.tobytes())
         if not spec.tied:
             q, s = quantize_q80(w["cls"], gs)
