@@ -55,6 +55,28 @@ def export_nano(model, out_path: str, quant: int = mf.QUANT_F32, gs: int = 128, 
     return mf.write_model_from_weights(out_path, spec, quant, gs, weights_from_nano_state_dict(sd, spec), tok, rope=rope)
 
 
+def export_lora(lora_state_dict, lora_rank: int, lora_alpha: int, base_config, out_path: str) -> dict:
+    """A LoRA plug-in (the `lora` entry of a reference LoRA checkpoint: keys `layers.<l>.attention.w{q,k,v,o}.lora_{a,b}.weight`) in the
+    layout parse_lora_file reads (infer.c:436-500), as export.py:117-226 writes it: 256-byte header, then per projection the A
+    factors of all layers followed by the B factors."""
+    import struct
+    n_kv = base_config.n_kv_head if getattr(base_config, "n_kv_head", None) is not None else base_config.n_head
+    hdr = struct.pack("<II", 0x42443453, 0x55524C4D) + struct.pack("<12i", 2024, 10, 10, 32, int(lora_rank), int(lora_alpha), int(base_config.n_layer),
+                                                                  int(base_config.n_embd), int(base_config.n_head), int(n_kv), int(base_config.n_hidden), 0)
+    hdr += b"\0" * (256 - len(hdr))
+    parts = [hdr]
+    for proj in ("wq", "wk", "wv", "wo"):
+        for fac in ("lora_a", "lora_b"):
+            keys = sorted((k for k in lora_state_dict if f"{proj}.{fac}" in k), key=lambda k: int(k.split(".")[1]))
+            assert len(keys) == int(base_config.n_layer), f"{proj}.{fac}: {len(keys)} tensors for {base_config.n_layer} layers"
+            for k in keys:
+                parts.append(np.ascontiguousarray(lora_state_dict[k].detach().to("cpu").float().numpy(), np.float32).tobytes())
+    blob = b"".join(parts)
+    with open(out_path, "wb") as f:
+        f.write(blob)
+    return {"path": out_path, "bytes": len(blob)}
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("checkpoint"); ap.add_argument("out")

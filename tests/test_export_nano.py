@@ -74,3 +74,39 @@ def test_export_is_byte_identical_to_the_reference_exporter_and_matches_the_mode
     a, b = open(oursq, "rb").read(), open(theirsq, "rb").read()
     assert len(a) == len(b), (len(a), len(b))
     assert a == b, "Q80 export differs from the reference exporter at byte %d" % next(i for i in range(len(a)) if a[i] != b[i])
+
+
+def test_lora_export_is_byte_identical_and_the_reference_engine_reproduces_the_lora_model(tmp_path, ref_modules):
+    """export.py:117-226 / infer.c:436-500 and the LoRA branches infer.c:792-808, :898-903: base file + plug-in run by the unmodified
+    reference engine against the PyTorch model with the same low-rank branches attached."""
+    ref_model, ref_export = ref_modules
+    m = tiny_gpt(ref_model, seed=9)
+    V = m.config.vocab_size
+    tok = {"itos": [chr(0x4E00 + i) for i in range(V)], "vocab_size": V, "special_tokens": []}
+    base = str(tmp_path / "base.bin")
+    export_nano.export_nano(m, base, mf.QUANT_F32, tokenizer_config=tok)           # the base model, before the branches are attached
+    m.to_lora(lora_rank=4, lora_alpha=8)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_b" in n:
+                p.copy_(0.05 * torch.randn_like(p))                                  # B starts at zero: make the branch contribute
+    m.eval()
+    lora_sd = m.get_lora_state_dict()
+    ours, theirs = str(tmp_path / "lora_ours.bin"), str(tmp_path / "lora_theirs.bin")
+    export_nano.export_lora(lora_sd, 4, 8, m.config, ours)
+    ref_export.export_lora(lora_sd, {"lora_rank": 4, "lora_alpha": 8}, m.config, theirs)
+    a, b = open(ours, "rb").read(), open(theirs, "rb").read()
+    assert a == b, "LoRA export differs from the reference exporter"
+    if not ob.ref_available("strict"):
+        pytest.skip("oracle/_ref not built: byte identity checked only")
+    toks = mf.teacher_tokens(S, V)
+    with torch.no_grad():
+        want = np.stack([m(torch.tensor([list(map(int, toks[: p + 1]))], dtype=torch.long))[0][0, -1].float().numpy() for p in range(S)])
+    r = ob.RefEngine(base, S)
+    r.load_lora(a)
+    got = np.stack([r.forward(int(toks[p]), p) for p in range(S)])
+    r.close()
+    err, scale = float(np.abs(got - want).max()), float(np.abs(want).max())
+    print(f"reference engine (base file + exported plug-in) vs the PyTorch LoRA model: max|dlogit| {err:.3e} (logit scale {scale:.2f})")
+    assert err < 2e-4 * max(1.0, scale)
